@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- DE+PSD channel-windows/s of the fused front end on N B200s, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--subjects S] [--mode 500ms|1s|2s]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference [--gpus N --steps K --warmup W]
+
+Workload (BASELINE.json configs[1] at cohort scale, north_star): 500 ms sliding windows (250 ms hop, 7 per 2 s
+clip) cut straight out of raw synthetic SEED-DV recordings (62 ch, 200 Hz, 7 blocks x 104000 samples per
+subject), S subjects resident per GPU (weak scaling: per-GPU work is fixed as N grows).  One *step* = one pass
+of the fused kernel over the whole resident batch = S * 607600 channel-windows.  The batch (S * 180.5 MB) is
+many times the 126 MB L2, so no L2 flush is needed between steps.
+
+One JSON line is printed by rank 0; see the README section "Benchmark" / DESIGN.md "Measurement" for the keys.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CW_PER_SUBJECT = {"500ms": 7 * 40 * 5 * 7 * 62, "1s": 7 * 40 * 5 * 2 * 62, "2s": 7 * 40 * 5 * 62}
+# algorithmic bytes per channel-window (SURVEY.md 8d / BASELINE.md 4): live input samples + 40 B of features
+BYTES_PER_CW = {"500ms": 1600.0 / 7 + 40, "1s": 840.0, "2s": 840.0}
+METRIC = "de_psd_channel_windows_per_s"
+UNIT = "channel-windows/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's loop-for-loop port of the reference (oracle.de_psd_loop), one process per host core
+# ---------------------------------------------------------------------------------------------------------------
+_CPU_CLIPS = None
+
+
+def _cpu_init(path):
+    global _CPU_CLIPS
+    import numpy as np
+    _CPU_CLIPS = np.load(path, mmap_mode="r")
+
+
+def _cpu_work(args):
+    """Reference arithmetic for `n` clips starting at `first` (500 ms driver loop, 1per500ms.py:20-27)."""
+    first, n, mode = args
+    import numpy as np
+    import oracle
+    clips = _CPU_CLIPS
+    done = 0
+    for i in range(first, first + n):
+        clip = np.asarray(clips[i % clips.shape[0]])
+        if mode == "500ms":
+            for w in range(7):
+                oracle.de_psd_loop(clip[:, 50 * w:50 * w + 100], 200, 0.5)
+            done += 7 * clip.shape[0]
+        elif mode == "1s":
+            oracle.de_psd_loop(clip[:, :200], 200, 1)
+            oracle.de_psd_loop(clip[:, 200:], 200, 1)
+            done += 2 * clip.shape[0]
+        else:
+            oracle.de_psd_loop(clip, 200, 2)
+            done += clip.shape[0]
+    return done
+
+
+class CpuArm:
+    """Pool of worker processes running the reference's per-channel Python loops on a bounded sample of clips."""
+
+    def __init__(self, mode, n_sample_clips=200):
+        import numpy as np
+        import torch
+        from eeg2video_b200 import synth
+        import oracle
+        self.mode = mode
+        try:
+            self.cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            self.cores = os.cpu_count() or 1
+        raw = synth.synth_blocks(1, 1001, device="cpu").numpy()                      # one block, (1, 62, 104000)
+        padded = np.concatenate([raw, np.zeros((6,) + raw.shape[1:], np.float32)])
+        clips = oracle.segment_subject(padded)[0].reshape(200, 62, 400)[:n_sample_clips]
+        self.tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
+        np.save(self.tmp.name, clips)
+        self.n_clips = clips.shape[0]
+        torch.set_num_threads(1)
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(self.tmp.name,))
+        self.pool.map(_cpu_work, [(0, 1, mode)] * self.cores)                          # start-up, untimed
+
+    def run(self, clips_per_worker):
+        """Every worker processes `clips_per_worker` clips; returns (channel-windows, seconds)."""
+        jobs = [(w * clips_per_worker, clips_per_worker, self.mode) for w in range(self.cores)]
+        t0 = time.perf_counter()
+        done = sum(self.pool.map(_cpu_work, jobs, chunksize=1))
+        return done, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        os.unlink(self.tmp.name)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (its Python loops, restated in
+    oracle/de_psd.py -- the reference itself is Python and cannot travel to the GPU box), all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    arm = CpuArm(args.mode)
+    per_step = args.cpu_clips_per_step
+    for _ in range(args.warmup):
+        arm.run(max(1, per_step // 4))
+    total_cw, total_s = 0, 0.0
+    for _ in range(args.steps):
+        cw, s = arm.run(per_step)
+        total_cw += cw
+        total_s += s
+    arm.close()
+    value = total_cw / total_s
+    sample = (f"{args.steps} steps x {arm.cores} workers x {per_step} synthetic 2 s clips (62 ch) each, "
+              f"mode {args.mode}, oracle.de_psd_loop (loop-for-loop port of DE_PSD.py:8-71)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def workload_config(args, geometry):
+    cfg = {
+        "workload": f"extract_DE_PSD_features_1per{args.mode} fused with segmentation from raw SEED-DV-shaped "
+                    f"recordings (BASELINE configs[1] at cohort scale, configs[3] sharding)",
+        "mode": args.mode, "subjects_per_gpu": args.subjects, "blocks_per_subject": 7, "channels": 62,
+        "fs_hz": 200, "block_len": 104000,
+        "channel_windows_per_step_per_gpu": args.subjects * CW_PER_SUBJECT[args.mode],
+        "l2_policy": f"inputs larger than L2 ({args.subjects * 180.544:.0f} MB resident batch per GPU vs 126 MB L2)",
+        "parallelism": f"subjects sharded over {args.gpus} GPU(s), no data-path collective",
+    }
+    if geometry:
+        cfg["kernel_geometry"] = geometry
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md clocks line)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.out = None
+
+    def start(self):
+        try:
+            self.out = tempfile.NamedTemporaryFile(mode="w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.gpu_index)], stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.out.flush()
+        self.out.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        for row in self.out.read().strip().splitlines():
+            cells = [c.strip() for c in row.split(",")]
+            if len(cells) < 9:
+                continue
+            try:
+                sm.append(float(cells[1]))
+                smax.append(float(cells[2]))
+                power.append(float(cells[3]))
+            except ValueError:
+                continue
+            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                  cells[5:9]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        self.out.close()
+        os.unlink(self.out.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture, scaled
+    to this run's launch size by the profile's own bytes-per-channel-window (None until a capture exists)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rec = json.load(f).get(mode)
+    return rec
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from eeg2video_b200 import _lib, cohort, frontend, ops, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    mode = args.mode
+    mode_id = frontend.MODES[mode]
+    S = args.subjects
+    cw_step_gpu = S * CW_PER_SUBJECT[mode]
+
+    # ---- resident synthetic batch: this rank's subjects (global ids rank*S .. rank*S+S-1) ----
+    raw = synth.synth_cohort(range(rank * S, rank * S + S), dev).reshape(S * 7, 62, 104000)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity gate on this rank's first subject (oracle = checker only) ----
+    parity = None
+    if rank == 0 and not args.skip_parity:
+        import numpy as np
+        import oracle
+        blocks = raw[:1]
+        de, psd, _ = ops.de_psd_from_raw(blocks, mode_id)
+        padded = np.concatenate([blocks.cpu().numpy(), np.zeros((6, 62, 104000), np.float32)])
+        clips = oracle.segment_subject(padded)[0]
+        seg_ok = bool(np.array_equal(ops.segment_clips(blocks, 200).cpu().numpy().reshape(clips.shape), clips))
+        win, hop, nwin, tw = {"500ms": (100, 50, 7, 0.5), "1s": (200, 200, 2, 1), "2s": (400, 0, 1, 2)}[mode]
+        wins = np.stack([clips[..., w * hop:w * hop + win] for w in range(nwin)], axis=2)   # (40,5,W,62,win)
+        de_ref, psd_ref = oracle.de_psd_closed_form(wins, 200, tw)
+        got_de = de.cpu().numpy().reshape(de_ref.shape)
+        got_psd = psd.cpu().numpy().reshape(psd_ref.shape)
+        parity = {"segmentation_bit_exact": seg_ok,
+                  "psd_max_rel": float(np.max(np.abs(got_psd - psd_ref) / psd_ref)),
+                  "de_max_abs": float(np.max(np.abs(got_de - de_ref))),
+                  "checked_channel_windows": int(de_ref.size // 5)}
+        if not (seg_ok and parity["psd_max_rel"] <= 1e-4 and parity["de_max_abs"] <= 1e-4):
+            raise SystemExit(f"parity gate failed: {parity}")
+
+    # ---- device-resident throughput: K launches of the fused kernel, CUDA events on the launch stream ----
+    with torch.cuda.device(dev):
+        de_buf = torch.empty((S * 7 * 200, ops.WINDOWS_PER_CLIP[mode_id], 62, 5), dtype=torch.float32, device=dev)
+        psd_buf = torch.empty_like(de_buf)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        _lib.check(lib.eegfe_de_psd_from_raw(raw.data_ptr(), raw.shape[0], 62, 104000, raw.stride(0), raw.stride(1),
+                                             mode_id, de_buf.data_ptr(), psd_buf.data_ptr(), status.data_ptr(),
+                                             stream.cuda_stream))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches_before = _lib.launch_count()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    gpu_launches = _lib.launch_count() - launches_before
+    # keep the same launches running (untimed) long enough for nvidia-smi to see the clocks under this load
+    if rank == 0:
+        t_end = time.perf_counter() + args.clock_probe_s
+        while time.perf_counter() < t_end:
+            for _ in range(10):
+                step()
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["sampled_over"] = f"timed region + {args.clock_probe_s:.1f} s continuation of the same launches"
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * cw_step_gpu * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end: pinned host recordings -> H2D -> fused kernel -> D2H of the features, every step ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    pipe = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode)
+    raw_host = torch.empty((S * 7, 62, 104000), dtype=torch.float32).pin_memory()
+    raw_host.copy_(raw)
+    de_host = torch.empty(pipe.feature_shape(S * 7), dtype=torch.float32).pin_memory()
+    psd_host = torch.empty_like(de_host).pin_memory()
+    pipe.run(raw_host, de_host, psd_host)                                   # warm-up
+    barrier()
+    launches_e2e0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pipe.run(raw_host, de_host, psd_host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * cw_step_gpu * e2e_steps / e2e_s
+    e2e_ok = bool(torch.equal(de_host, de_buf.cpu())) if rank == 0 else True
+    e2e_launches = _lib.launch_count() - launches_e2e0
+
+    # ---- final gather of the feature tensors to rank 0 (the only collective; reported, not in `value`) ----
+    gather = None
+    if world > 1:
+        shape = (S,) + tuple(de_buf.shape)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full_de = cohort.gather_to_rank0(de_buf.reshape((S, -1)), S * world)
+        full_psd = cohort.gather_to_rank0(psd_buf.reshape((S, -1)), S * world)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        nbytes = 2 * de_buf.numel() * 4 * (world - 1)
+        gather = {"ms": float(gms.item()), "bytes_into_rank0": nbytes,
+                  "gbs_into_rank0": nbytes / (float(gms.item()) * 1e-3) / 1e9,
+                  "value_with_gather": world * cw_step_gpu / ((elapsed_ms / args.steps + float(gms.item())) * 1e-3)}
+        del full_de, full_psd, shape
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kernel_ms = elapsed_ms / args.steps                       # one launch per step
+        achieved = cw_step_gpu * BYTES_PER_CW[mode] / (kernel_ms * 1e-3) / 1e9
+        traffic = profiled_traffic(mode)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None if traffic is None else traffic["dram_bytes_per_cw"] * cw_step_gpu,
+                    "peak_source": peak_src, "kernel": "eegfe::de_psd_kernel<Cfg500ms>" if mode == "500ms" else
+                    "eegfe::de_psd_kernel", "kernel_ms": kernel_ms,
+                    "algorithmic_bytes_per_channel_window": BYTES_PER_CW[mode],
+                    "note": "500 ms mode is bounded by the FP32 pipe, not HBM (DESIGN.md 'Rooflines')"
+                    if mode == "500ms" else ""}
+        cpu = None
+        if not args.skip_cpu_baseline and world == 1:
+            arm = CpuArm(mode)
+            cw, s = arm.run(args.cpu_clips_per_step * 4)
+            arm.close()
+            cpu = {"value": cw / s, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                   "sample": f"{arm.cores} workers x {args.cpu_clips_per_step * 4} synthetic 2 s clips (62 ch) each, "
+                             f"mode {mode}, oracle.de_psd_loop (loop-for-loop port of DE_PSD.py:8-71), {s:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, _lib.launch_geometry(mode_id)),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(raw_host.numel() * 4),
+                    "d2h_bytes_per_step": int(2 * de_host.numel() * 4), "steps": e2e_steps,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_result": e2e_ok,
+                    "path": "pinned host -> HostPipeline (chunked H2D / fused kernel / D2H on 3 streams) -> pinned host"},
+            "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        }
+        if gather:
+            line["gather"] = gather
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--mode", default="500ms", choices=("500ms", "1s", "2s"))
+    ap.add_argument("--subjects", type=int, default=24, help="subjects resident per GPU (one step = all of them)")
+    ap.add_argument("--chunk-blocks", type=int, default=28, help="blocks per in-flight chunk of the e2e pipeline")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-clips-per-step", type=int, default=40, help="clips per worker per CPU step")
+    ap.add_argument("--clock-probe-s", type=float, default=1.5)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

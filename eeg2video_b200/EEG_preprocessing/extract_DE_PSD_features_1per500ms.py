@@ -1,0 +1,74 @@
+"""500 ms sliding-window DE/PSD driver -- drop-in for
+/root/reference/EEG_preprocessing/extract_DE_PSD_features_1per500ms.py (same CLI flags and defaults).
+"""
+import argparse
+import os
+
+import numpy as np
+
+from .. import frontend
+from . import _io
+
+
+def _clips_behind_window_view(raw):
+    """If ``raw`` is the strided view seg_sliding_window(clips, 0.5, 0.25) returns, recover ``clips`` (no copy),
+    so that the fused kernel reads 1600 B per channel-clip instead of a materialised 2800 B."""
+    if raw.ndim != 6 or raw.shape[3] != 7 or raw.shape[5] != 100:
+        return None
+    if _io.is_torch(raw):
+        st, unit = raw.stride(), 1
+        if st[5] != unit or st[3] != 50 * unit or st[4] != 400 * unit:
+            return None
+        return raw.as_strided(raw.shape[:3] + (raw.shape[4], 400), (st[0], st[1], st[2], st[4], st[5]),
+                              raw.storage_offset())
+    st, unit = raw.strides, raw.itemsize
+    if st[5] != unit or st[3] != 50 * unit or st[4] != 400 * unit:
+        return None
+    return np.lib.stride_tricks.as_strided(raw, shape=raw.shape[:3] + (raw.shape[4], 400),
+                                           strides=(st[0], st[1], st[2], st[4], st[5]), writeable=False)
+
+
+def extract_de_psd_sw(raw, fs, win_sec):
+    """(B, C, R, W, ch, L) windows -> (DE, PSD), each (B, C, R, W, ch, 5) float32 (reference :12-29)."""
+    _io.check_fs(fs)
+    if raw.ndim != 6:
+        raise ValueError("raw must be (blocks, concepts, repetitions, windows, channels, samples)")
+    length = int(win_sec * fs)
+    if raw.shape[5] != length:
+        raise ValueError(f"operands could not be broadcast together with shapes ({raw.shape[5]},) ({length},) ")
+    if length not in (100, 200, 400):
+        raise NotImplementedError(f"win_sec={win_sec!r}: supported window lengths are 0.5, 1 and 2 s")
+    like_torch = _io.is_torch(raw)
+    clips = _clips_behind_window_view(raw) if length == 100 else None
+    if clips is not None:
+        de, psd = frontend.de_psd_from_clips(_io.to_device_f32(clips), "500ms", check=True)
+    else:
+        de, psd = frontend.de_psd_windows(_io.to_device_f32(raw), check=True)
+    return _io.finish((de, psd), like_torch, np.float32)
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--raw_dir', default="./data/Preprocessing/Segmented_500ms_sw", help='windowed raw EEG .npy folder')
+    parser.add_argument('--de_dir', default="./data/Preprocessing/DE_500ms_sw", help='where DE is saved')
+    parser.add_argument('--psd_dir', default="./data/Preprocessing/PSD_500ms_sw", help='where PSD is saved')
+    parser.add_argument('--subs', nargs='+', type=int, default=list(range(1, 21)), help='subject numbers')
+    args = parser.parse_args()
+
+    FS = 200
+    WIN_SEC = 0.5
+
+    os.makedirs(args.de_dir, exist_ok=True)
+    os.makedirs(args.psd_dir, exist_ok=True)
+
+    for sub in args.subs:
+        raw_path = os.path.join(args.raw_dir, f'sub{sub}.npy')
+        de_out_path = os.path.join(args.de_dir, f'sub{sub}.npy')
+        psd_out_path = os.path.join(args.psd_dir, f'sub{sub}.npy')
+        print(f"Processing subject {sub}...")
+
+        raw = np.load(raw_path)
+        DE_data, PSD_data = extract_de_psd_sw(raw, FS, WIN_SEC)
+        np.save(de_out_path, DE_data)
+        np.save(psd_out_path, PSD_data)
+        print(f"Saved DE/PSD: {os.path.basename(de_out_path)} / {os.path.basename(psd_out_path)}")

@@ -1,0 +1,149 @@
+"""torch.library custom ops over the extern "C" launchers of libeegfe.so.
+
+PyTorch is plumbing here: it owns device memory and streams; all arithmetic happens in the CUDA library.
+Every op is CUDA-only -- a CPU tensor is an error, not a fallback.
+
+    eeg2video::de_psd_from_raw(raw, mode)     -> (de, psd, status)
+    eeg2video::de_psd_from_clips(clips, mode) -> (de, psd, status)
+    eeg2video::de_psd_windows(x)              -> (de, psd, status)
+    eeg2video::segment_clips(raw, fs)         -> clips
+    eeg2video::sliding_windows(clips)         -> windows
+
+`status` is a 1-element int32 device tensor (see EEGFE_STATUS_* in include/eegfe.h); reading it is the caller's
+choice, so that throughput paths never synchronise.
+"""
+from typing import Tuple
+
+import torch
+
+from . import _lib
+
+WINDOWS_PER_CLIP = {_lib.MODE_500MS: 7, _lib.MODE_1S: 2, _lib.MODE_2S: 1}
+
+_COPY_DTYPES = {
+    torch.float32: _lib.DTYPE_F32, torch.float64: _lib.DTYPE_F64,
+    torch.float16: _lib.DTYPE_F16, torch.int16: _lib.DTYPE_I16,
+}
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"eeg2video ops are CUDA-only (no CPU fallback): `{name}` is on {t.device}")
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+@torch.library.custom_op("eeg2video::de_psd_from_raw", mutates_args=(), device_types="cuda")
+def de_psd_from_raw(raw: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """raw float32 (n_blocks, n_ch, T), last axis contiguous -> de, psd float32 (n_blocks*200, W, n_ch, 5)."""
+    _require_cuda(raw, "raw")
+    if raw.dim() != 3 or raw.dtype != torch.float32 or (raw.shape[2] > 1 and raw.stride(2) != 1):
+        raise ValueError("raw must be float32 (n_blocks, n_ch, T) with a contiguous time axis")
+    if mode not in WINDOWS_PER_CLIP:
+        raise ValueError(f"unknown mode {mode}")
+    n_blocks, n_ch, t_len = raw.shape
+    n_win = WINDOWS_PER_CLIP[mode]
+    with torch.cuda.device(raw.device):
+        de = torch.empty((n_blocks * 200, n_win, n_ch, 5), dtype=torch.float32, device=raw.device)
+        psd = torch.empty_like(de)
+        status = torch.zeros(1, dtype=torch.int32, device=raw.device)
+        _lib.check(_lib.load().eegfe_de_psd_from_raw(
+            raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), mode,
+            de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
+    return de, psd, status
+
+
+@de_psd_from_raw.register_fake
+def _(raw, mode):
+    n_win = WINDOWS_PER_CLIP[mode]
+    de = raw.new_empty((raw.shape[0] * 200, n_win, raw.shape[1], 5), dtype=torch.float32)
+    return de, torch.empty_like(de), raw.new_empty((1,), dtype=torch.int32)
+
+
+@torch.library.custom_op("eeg2video::de_psd_from_clips", mutates_args=(), device_types="cuda")
+def de_psd_from_clips(clips: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """clips float32 contiguous (n_clips, n_ch, 400) -> de, psd float32 (n_clips, W, n_ch, 5)."""
+    _require_cuda(clips, "clips")
+    if clips.dim() != 3 or clips.shape[2] != 400 or clips.dtype != torch.float32 or not clips.is_contiguous():
+        raise ValueError("clips must be contiguous float32 (n_clips, n_ch, 400)")
+    if mode not in WINDOWS_PER_CLIP:
+        raise ValueError(f"unknown mode {mode}")
+    n_clips, n_ch, _ = clips.shape
+    n_win = WINDOWS_PER_CLIP[mode]
+    with torch.cuda.device(clips.device):
+        de = torch.empty((n_clips, n_win, n_ch, 5), dtype=torch.float32, device=clips.device)
+        psd = torch.empty_like(de)
+        status = torch.zeros(1, dtype=torch.int32, device=clips.device)
+        _lib.check(_lib.load().eegfe_de_psd_from_clips(
+            clips.data_ptr(), n_clips, n_ch, mode, de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(clips)))
+    return de, psd, status
+
+
+@de_psd_from_clips.register_fake
+def _(clips, mode):
+    de = clips.new_empty((clips.shape[0], WINDOWS_PER_CLIP[mode], clips.shape[1], 5), dtype=torch.float32)
+    return de, torch.empty_like(de), clips.new_empty((1,), dtype=torch.int32)
+
+
+@torch.library.custom_op("eeg2video::de_psd_windows", mutates_args=(), device_types="cuda")
+def de_psd_windows(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x float32 (n_rows, L), L in {100, 200, 400}, unit stride along L -> de, psd float32 (n_rows, 5)."""
+    _require_cuda(x, "x")
+    if x.dim() != 2 or x.dtype != torch.float32 or x.shape[1] not in (100, 200, 400) or x.stride(1) != 1:
+        raise ValueError("x must be float32 (n_rows, L) with L in {100, 200, 400} and unit stride along L")
+    n_rows, length = x.shape
+    row_stride = x.stride(0) if n_rows > 1 else length
+    with torch.cuda.device(x.device):
+        de = torch.empty((n_rows, 5), dtype=torch.float32, device=x.device)
+        psd = torch.empty_like(de)
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.check(_lib.load().eegfe_de_psd_windows(
+            x.data_ptr(), n_rows, length, row_stride, de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(x)))
+    return de, psd, status
+
+
+@de_psd_windows.register_fake
+def _(x):
+    de = x.new_empty((x.shape[0], 5), dtype=torch.float32)
+    return de, torch.empty_like(de), x.new_empty((1,), dtype=torch.int32)
+
+
+@torch.library.custom_op("eeg2video::segment_clips", mutates_args=(), device_types="cuda")
+def segment_clips(raw: torch.Tensor, fs: int) -> torch.Tensor:
+    """raw (n_blocks, n_ch, T) of a 2/4/8-byte dtype -> clips (n_blocks*200, n_ch, 2*fs), bit-exact gather."""
+    _require_cuda(raw, "raw")
+    if raw.dim() != 3 or raw.dtype not in _COPY_DTYPES or (raw.shape[2] > 1 and raw.stride(2) != 1):
+        raise ValueError("raw must be (n_blocks, n_ch, T) float32/float64/float16/int16 with a contiguous time axis")
+    n_blocks, n_ch, t_len = raw.shape
+    with torch.cuda.device(raw.device):
+        clips = torch.empty((n_blocks * 200, n_ch, 2 * fs), dtype=raw.dtype, device=raw.device)
+        _lib.check(_lib.load().eegfe_segment_clips(
+            raw.data_ptr(), _COPY_DTYPES[raw.dtype], n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), fs,
+            clips.data_ptr(), _stream(raw)))
+    return clips
+
+
+@segment_clips.register_fake
+def _(raw, fs):
+    return raw.new_empty((raw.shape[0] * 200, raw.shape[1], 2 * fs))
+
+
+@torch.library.custom_op("eeg2video::sliding_windows", mutates_args=(), device_types="cuda")
+def sliding_windows(clips: torch.Tensor) -> torch.Tensor:
+    """clips contiguous (n_clips, n_ch, 400) -> windows (n_clips, 7, n_ch, 100), bit-exact gather."""
+    _require_cuda(clips, "clips")
+    if clips.dim() != 3 or clips.shape[2] != 400 or clips.dtype not in _COPY_DTYPES or not clips.is_contiguous():
+        raise ValueError("clips must be contiguous (n_clips, n_ch, 400) float32/float64/float16/int16")
+    n_clips, n_ch, _ = clips.shape
+    with torch.cuda.device(clips.device):
+        out = torch.empty((n_clips, 7, n_ch, 100), dtype=clips.dtype, device=clips.device)
+        _lib.check(_lib.load().eegfe_sliding_windows(
+            clips.data_ptr(), _COPY_DTYPES[clips.dtype], n_clips, n_ch, out.data_ptr(), _stream(clips)))
+    return out
+
+
+@sliding_windows.register_fake
+def _(clips):
+    return clips.new_empty((clips.shape[0], 7, clips.shape[1], 100))

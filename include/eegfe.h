@@ -1,0 +1,122 @@
+/*
+ * eegfe.h -- C ABI of libeegfe.so, the B200 (sm_100a) EEG feature front end.
+ *
+ * Drop-in boundary for the hot path of gaspachoo/EEG2Video's EEG_preprocessing package.  The reference has no
+ * FFI layer of its own (it is pure Python); each entry point below therefore names the Python function whose
+ * arithmetic it replaces, and eeg2video_b200/EEG_preprocessing/ mirrors those functions one-to-one on top of
+ * this ABI (INTEGRATION.md shows the ctypes binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers, borrowed for the duration of the call, never freed or retained.
+ *   - Every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *     No hidden allocation, no host synchronisation.
+ *   - Return value: 0 on success, a negative EEGFE_E* code for argument errors, or a positive cudaError_t.
+ *     eegfe_error_string() turns either into text.
+ *   - `status` (optional, may be NULL) points to one device int that the kernels OR flags into:
+ *     EEGFE_STATUS_ZERO_POWER is set when some band has zero power, i.e. where the reference raises
+ *     ValueError("math domain error") at DE_PSD.py:68.  The caller zeroes it and reads it back.
+ *   - Feature layout is the reference's: for unit u (a clip or a pre-cut window group), window w, channel c,
+ *     band b the value sits at  out[((u * n_windows + w) * n_ch + c) * 5 + b]  -- i.e. the
+ *     (block, concept, repetition[, window], channel, band) arrays of the extract_DE_PSD_features_* drivers
+ *     with the leading axes flattened.  Bands: delta, theta, alpha, beta, gamma (DE_PSD.py:28-29).
+ *   - Sampling rate is fixed at 200 Hz (the only rate the reference's drivers use; FFT length 200, DE_PSD.py:27).
+ */
+#ifndef EEGFE_H_
+#define EEGFE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EEGFE_ABI_VERSION 1
+
+/* analysis modes */
+#define EEGFE_MODE_500MS 0 /* 7 windows of 100 samples, hop 50, Hann(100), zero-padded to 200 (1per500ms driver) */
+#define EEGFE_MODE_1S 1    /* 2 windows of 200 samples, Hann(200)                               (1per1s script)  */
+#define EEGFE_MODE_2S 2    /* 1 window: first 200 samples weighted by the head of Hann(400)     (1per2s driver)  */
+
+/* argument errors */
+#define EEGFE_EINVAL (-1)   /* bad mode / shape / null pointer                       */
+#define EEGFE_ERANGE (-2)   /* block too short for the requested segments            */
+#define EEGFE_EDTYPE (-3)   /* unsupported element type                              */
+
+/* status flags */
+#define EEGFE_STATUS_ZERO_POWER 1
+
+/* element types for the byte-copy (segmentation) entry points */
+#define EEGFE_DTYPE_F32 0
+#define EEGFE_DTYPE_F64 1
+#define EEGFE_DTYPE_F16 2
+#define EEGFE_DTYPE_I16 3
+
+int eegfe_abi_version(void);
+const char* eegfe_error_string(int code);
+
+/* Number of analysis windows per clip in `mode` (7, 2, 1), or EEGFE_EINVAL. */
+int eegfe_windows_per_clip(int mode);
+
+/*
+ * Fused segmentation + DE/PSD straight from raw recordings.
+ * Replaces: segment_raw_signals_200Hz.py:15-70 (extract_2s_segment index arithmetic, :58-65),
+ *           segment_sliding_window.py:6-21, DE_PSD.py:8-71 and the loops of
+ *           extract_DE_PSD_features_1per2s.py:16-28 / _1per1s.py:24-58 / _1per500ms.py:12-29.
+ *
+ * raw          float32 [n_blocks][n_ch][block_len] with strides (block_stride, ch_stride, 1) in elements;
+ *              a "block" is one 8 min 40 s recording block of one subject (n_blocks = subjects * 7).
+ * block_len    samples per row; must be >= 40 * 2600 = 104000 (else EEGFE_ERANGE, the reference's
+ *              RuntimeError("Segment length mismatch"), segment_raw_signals_200Hz.py:68-69).
+ * de, psd      float32 [n_blocks * 200][n_windows][n_ch][5]; clip index = (block * 40 + concept) * 5 + repetition.
+ * No clip tensor is materialised: windows are cut by index arithmetic, clip (c, r) starting at sample
+ * c * 2600 + 600 + r * 400.
+ */
+int eegfe_de_psd_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len,
+                          int64_t block_stride, int64_t ch_stride, int mode,
+                          float* de, float* psd, int* status, void* stream);
+
+/*
+ * DE/PSD of already segmented 2 s clips.
+ * Replaces: extract_de_psd_raw (1per2s.py:16-28), the 1 s script body (1per1s.py:24-58) and -- fused with
+ *           seg_sliding_window -- extract_de_psd_sw (1per500ms.py:12-29).
+ * clips        float32 [n_clips][n_ch][400], contiguous.
+ * de, psd      float32 [n_clips][n_windows][n_ch][5].
+ */
+int eegfe_de_psd_from_clips(const float* clips, int64_t n_clips, int n_ch, int mode,
+                            float* de, float* psd, int* status, void* stream);
+
+/*
+ * DE/PSD of pre-cut windows: the DE_PSD(data, 200, time_window) call itself (DE_PSD.py:8-71) and
+ * extract_de_psd_sw on a materialised (.., 7, 62, 100) tensor (1per500ms.py:24-25).
+ * x            float32 [n_rows][win_len] with row stride `row_stride` elements (>= win_len);
+ *              win_len = 100 (0.5 s), 200 (1 s) or 400 (2 s).
+ * de, psd      float32 [n_rows][5].
+ */
+int eegfe_de_psd_windows(const float* x, int64_t n_rows, int win_len, int64_t row_stride,
+                         float* de, float* psd, int* status, void* stream);
+
+/*
+ * Materialised segmentation (the .npy-producing scripts): byte-exact gathers, any 2/4/8-byte element type.
+ * Replaces: segment_all_files (segment_raw_signals_200Hz.py:73-110)
+ * raw -> clips [n_blocks * 200][n_ch][2 fs]; `fs` is the reference's sampling-rate argument (clip (c, r) starts
+ * at c * 13 fs + 3 fs + r * 2 fs and block_len must be >= 40 * 13 fs).
+ */
+int eegfe_segment_clips(const void* raw, int dtype, int64_t n_blocks, int n_ch, int64_t block_len,
+                        int64_t block_stride, int64_t ch_stride, int fs, void* clips, void* stream);
+
+/*
+ * Replaces: seg_sliding_window + np.save copy (segment_sliding_window.py:6-21, :55) for win 100 / hop 50:
+ * clips [n_clips][n_ch][400] -> windows [n_clips][7][n_ch][100]
+ */
+int eegfe_sliding_windows(const void* clips, int dtype, int64_t n_clips, int n_ch, void* windows, void* stream);
+
+/* Introspection used by bench.py / tests: kernel launch geometry chosen for `mode` on the current device. */
+int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int* rows_per_tile);
+
+/* Number of kernels this library has launched since load (gpu_launches accounting in bench.py). */
+int64_t eegfe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEGFE_H_ */

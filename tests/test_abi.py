@@ -1,0 +1,81 @@
+"""The C-ABI shared library: it loads, exports every function include/eegfe.h declares, and answers the calls
+that need no GPU.  CPU only (no kernel is launched)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from eeg2video_b200 import _lib
+
+HEADER = os.path.join(ROOT, "include", "eegfe.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.findall(r"^\s*(?:const\s+char\*|int64_t|int)\s+(eegfe_\w+)\s*\(", text, flags=re.M)
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(_lib.LIB_PATH), "run python -m eeg2video_b200.build"
+    assert os.path.dirname(_lib.LIB_PATH) == os.path.join(ROOT, "eeg2video_b200")
+
+
+def test_every_declared_symbol_is_exported():
+    names = declared_functions()
+    assert len(names) >= 10
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(dll, name), f"{name} declared in eegfe.h but not exported"
+    assert sorted(names) == sorted(_lib.SIGNATURES), "ctypes binding table out of sync with eegfe.h"
+
+
+def test_header_argument_counts_match_binding():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        m = re.search(name + r"\s*\(([^)]*)\)", text)
+        assert m, name
+        args = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+        assert len(args) == len(argtypes), name
+
+
+def test_no_gpu_calls():
+    lib = _lib.load()
+    assert lib.eegfe_abi_version() == 1
+    assert [lib.eegfe_windows_per_clip(m) for m in (0, 1, 2)] == [7, 2, 1]
+    assert lib.eegfe_windows_per_clip(9) == _lib.EINVAL
+    assert lib.eegfe_error_string(0) == b"success"
+    assert lib.eegfe_error_string(_lib.ERANGE) == b"Segment length mismatch"
+    # argument validation happens before anything touches the device
+    assert lib.eegfe_de_psd_from_raw(None, 0, 62, 104000, 0, 104000, 0, None, None, None, None) == 0      # empty
+    assert lib.eegfe_de_psd_from_raw(None, 1, 62, 104000, 62 * 104000, 104000, 0, None, None, None, None) == _lib.EINVAL
+    assert lib.eegfe_de_psd_from_raw(None, 1, 62, 104000, 62 * 104000, 104000, 7, None, None, None, None) == _lib.EINVAL
+    assert lib.eegfe_de_psd_from_clips(None, 0, 62, 1, None, None, None, None) == 0
+    assert lib.eegfe_de_psd_windows(None, 0, 100, 100, None, None, None, None) == 0
+    assert lib.eegfe_de_psd_windows(None, 4, 150, 150, None, None, None, None) == _lib.EINVAL
+    assert lib.eegfe_segment_clips(None, 99, 1, 62, 104000, 0, 104000, 200, None, None) == _lib.EDTYPE
+    assert lib.eegfe_sliding_windows(None, 0, 0, 62, None, None) == 0
+    with pytest.raises(_lib.EegfeError, match="Segment length mismatch"):
+        _lib.check(_lib.ERANGE)
+    assert _lib.launch_count() == 0
+
+
+def test_block_too_short_is_erange():
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.eegfe_de_psd_from_raw(p, 1, 62, 103999, 62 * 103999, 103999, 0, p, p, None, None) == _lib.ERANGE
+    assert lib.eegfe_segment_clips(p, 0, 1, 62, 103999, 62 * 103999, 103999, 200, p, None) == _lib.ERANGE
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under eeg2video_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "eeg2video_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "hostemu" not in text or f == "cplx.cuh", f

@@ -1,0 +1,283 @@
+"""Parity of the CUDA path with the oracle and with the reference's golden vectors -- every call goes through the
+C ABI of libeegfe.so (via the torch.library ops / the reference-named shims).  Needs a B200: -m gpu.
+
+Bars (BASELINE.json north_star): segmentation bit-exact; PSD <= 1e-4 relative; DE <= 1e-4 absolute (log2).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import assert_features_close, decode
+from eeg2video_b200 import _lib, frontend, ops, synth
+from eeg2video_b200.EEG_preprocessing import segment_raw_signals_200Hz as seg
+from eeg2video_b200.EEG_preprocessing import segment_sliding_window as ssw
+from eeg2video_b200.EEG_preprocessing.DE_PSD import DE_PSD
+from eeg2video_b200.EEG_preprocessing.extract_DE_PSD_features_1per1s import extract_de_psd_1s
+from eeg2video_b200.EEG_preprocessing.extract_DE_PSD_features_1per2s import extract_de_psd_raw
+from eeg2video_b200.EEG_preprocessing.extract_DE_PSD_features_1per500ms import extract_de_psd_sw
+
+pytestmark = pytest.mark.gpu
+TW = {100: 0.5, 200: 1, 400: 2}
+DEV = "cuda:0"
+
+
+def test_native_library_is_the_one_in_tree():
+    lib = _lib.load()
+    assert lib.eegfe_abi_version() == 1
+    before = _lib.launch_count()
+    ops.de_psd_windows(torch.ones(4, 100, device=DEV) * 3)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == before + 1
+
+
+# ---- DE_PSD itself against the reference's golden outputs ---------------------------------------------------------
+@pytest.mark.parametrize("length", (100, 200, 400))
+@pytest.mark.parametrize("kind", ("white", "offset", "pink_tone", "small"))
+def test_de_psd_golden(golden, length, kind):
+    g = golden("de_psd_golden.npz")
+    key = f"L{length}_{kind}"
+    de, psd = DE_PSD(decode(g[key + "_codes"]), 200, TW[length])
+    assert isinstance(de, np.ndarray) and de.dtype == np.float64 and de.shape == (62, 5)
+    assert_features_close(de, psd, g[key + "_de"], g[key + "_psd"])
+
+
+def test_de_psd_impulse_known_answer(golden):
+    g = golden("de_psd_golden.npz")
+    de, psd = DE_PSD(g["impulse_x"], 200, 0.5)
+    assert_features_close(de, psd, g["impulse_de"], g["impulse_psd"])
+
+
+def test_de_psd_torch_in_torch_out():
+    x = torch.randn(62, 200, device=DEV) * 30
+    de, psd = DE_PSD(x, 200, 1)
+    assert de.is_cuda and de.dtype == torch.float64 and tuple(de.shape) == (62, 5)
+    de_ref, psd_ref = oracle.de_psd_closed_form(x.cpu().numpy(), 200, 1)
+    assert_features_close(de.cpu().numpy(), psd.cpu().numpy(), de_ref, psd_ref)
+
+
+@pytest.mark.parametrize("dtype", (np.float64, np.float16, np.int16, np.int32))
+def test_de_psd_input_dtypes(dtype):
+    rng = np.random.default_rng(3)
+    x = (rng.integers(-2000, 2000, (10, 100)) / 8.0).astype(dtype)
+    de, psd = DE_PSD(x, 200, 0.5)
+    de_ref, psd_ref = oracle.de_psd_closed_form(x.astype(np.float64), 200, 0.5)
+    assert_features_close(de, psd, de_ref, psd_ref)
+
+
+@pytest.mark.parametrize("length", (100, 200, 400))
+@pytest.mark.parametrize("n_rows", (1, 2, 31, 33, 63, 64, 65, 127, 129, 1000))
+def test_ragged_row_counts(length, n_rows):
+    """Tiles hold 32..128 rows: every partial-tile size must be handled."""
+    rng = np.random.default_rng(n_rows * 7 + length)
+    x = (30 * rng.standard_normal((n_rows, length)) + 5).astype(np.float32)
+    de, psd = DE_PSD(x, 200, TW[length])
+    de_ref, psd_ref = oracle.de_psd_closed_form(x, 200, TW[length])
+    assert_features_close(de, psd, de_ref, psd_ref)
+
+
+def test_zero_power_raises_like_the_reference():
+    x = np.ones((4, 200), np.float32)
+    x[2] = 0
+    with pytest.raises(ValueError, match="math domain error"):
+        DE_PSD(x, 200, 1)
+    with pytest.raises(ValueError, match="math domain error"):
+        oracle.de_psd_loop(x, 200, 1)
+
+
+def test_empty_inputs():
+    de, psd = DE_PSD(np.zeros((0, 100), np.float32), 200, 0.5)
+    assert de.shape == (0, 5) and psd.shape == (0, 5)
+    de, psd, _ = ops.de_psd_from_clips(torch.zeros(0, 62, 400, device=DEV), _lib.MODE_500MS)
+    assert tuple(de.shape) == (0, 7, 62, 5)
+
+
+def test_strided_rows_and_unaligned_rows():
+    """Row stride != length (a view into a wider buffer) and rows that are only 4-byte aligned (odd stride /
+    offset base): the first uses TMA bulk copies, the second the cooperative-load path; same numbers."""
+    rng = np.random.default_rng(11)
+    wide = torch.from_numpy((30 * rng.standard_normal((70, 404))).astype(np.float32)).to(DEV)
+    ref = oracle.de_psd_closed_form(wide[:, :100].cpu().numpy(), 200, 0.5)
+    de, psd, _ = ops.de_psd_windows(wide[:, :100])
+    assert_features_close(de.cpu().numpy(), psd.cpu().numpy(), *ref)
+    odd = torch.from_numpy((30 * rng.standard_normal((70, 203))).astype(np.float32)).to(DEV)
+    view = odd[:, 1:201]
+    ref = oracle.de_psd_closed_form(view.cpu().numpy(), 200, 1)
+    de, psd, _ = ops.de_psd_windows(view)
+    assert_features_close(de.cpu().numpy(), psd.cpu().numpy(), *ref)
+    aligned_copy = view.contiguous()
+    de2, psd2, _ = ops.de_psd_windows(aligned_copy)
+    assert torch.equal(de, de2) and torch.equal(psd, psd2)       # both load paths feed identical arithmetic
+
+
+# ---- drivers against the reference's golden outputs -----------------------------------------------------------------
+def test_drivers_golden(golden):
+    g = golden("drivers_golden.npz")
+    clips = decode(g["codes"])
+    de, psd = extract_de_psd_raw(clips, 200)
+    assert de.dtype == np.float32 and de.shape == (2, 2, 3, 62, 5)
+    assert_features_close(de, psd, g["de_2s"], g["psd_2s"])
+    de, psd = extract_de_psd_1s(clips, 200)
+    assert de.dtype == np.float64 and de.shape == (2, 2, 3, 2, 62, 5)
+    assert_features_close(de, psd, g["de_1s"], g["psd_1s"])
+    win_view = ssw.seg_sliding_window(clips, 0.5, 0.25, fs=200)
+    de, psd = extract_de_psd_sw(win_view, 200, 0.5)                      # strided view -> fused path
+    assert de.dtype == np.float32 and de.shape == (2, 2, 3, 7, 62, 5)
+    assert_features_close(de, psd, g["de_500ms"], g["psd_500ms"])
+    de_m, psd_m = extract_de_psd_sw(np.ascontiguousarray(win_view), 200, 0.5)   # materialised -> pre-cut path
+    assert np.array_equal(de, de_m) and np.array_equal(psd, psd_m)
+
+
+def test_one_second_script_golden(golden):
+    g = golden("script_1s_golden.npz")
+    clips = decode(g["clips_codes"])[None, None]
+    de, psd = extract_de_psd_1s(clips, 200)
+    assert_features_close(de[0, 0], psd[0, 0], g["de"], g["psd"])
+
+
+# ---- segmentation: bit-exact -------------------------------------------------------------------------------------------
+def _formula_raw(n_ch, n_t):
+    b = np.arange(7).reshape(7, 1, 1)
+    ch = np.arange(n_ch).reshape(1, n_ch, 1)
+    t = np.arange(n_t).reshape(1, 1, n_t)
+    return (((b * 7919 + ch * 104729 + t * 31) % 65536) - 32768).astype(np.int16)
+
+
+def test_segment_clips_golden_bit_exact(golden):
+    g = golden("segment_golden.npz")
+    raw = _formula_raw(int(g["n_ch"]), int(g["n_t"]))
+    clips = seg.segment_subject(raw)
+    assert clips.dtype == np.int16 and clips.shape == (7, 40, 5, int(g["n_ch"]), 400)
+    for (b, c, r), want in zip(g["picks"], g["segments"]):
+        assert np.array_equal(clips[b, c, r], want)
+    assert np.array_equal(clips, oracle.segment_subject(raw))
+
+
+@pytest.mark.parametrize("dtype", (np.float32, np.float64, np.float16, np.int16))
+@pytest.mark.parametrize("n_t", (104000, 104001, 104003, 110000))
+def test_segment_clips_dtypes_and_odd_lengths(dtype, n_t):
+    rng = np.random.default_rng(n_t)
+    raw = rng.integers(-30000, 30000, (7, 3, n_t)).astype(dtype)
+    assert np.array_equal(seg.segment_subject(raw), oracle.segment_subject(raw))
+
+
+def test_segment_all_files_roundtrip(tmp_path):
+    rng = np.random.default_rng(5)
+    raw = rng.standard_normal((7, 62, 104000)).astype(np.float32)
+    src, dst = tmp_path / "EEG", tmp_path / "out"
+    src.mkdir()
+    np.save(src / "sub7.npy", raw)
+    seg.segment_all_files(str(src), str(dst), 200)
+    got = np.load(dst / "sub7.npy")
+    assert got.dtype == np.float32 and np.array_equal(got, oracle.segment_subject(raw))
+
+
+def test_block_too_short():
+    raw = torch.zeros(1, 62, 103999, device=DEV)
+    with pytest.raises(RuntimeError, match="Segment length mismatch"):
+        frontend.de_psd_from_raw(raw, "500ms")
+    with pytest.raises(RuntimeError, match="Segment length mismatch"):
+        ops.segment_clips(raw, 200)
+    with pytest.raises(RuntimeError, match="Segment length mismatch"):
+        seg.segment_subject(np.zeros((7, 2, 1000), np.float32))
+
+
+def test_sliding_windows_materialised_bit_exact():
+    rng = np.random.default_rng(9)
+    for dtype in (np.float32, np.float64, np.int16):
+        clips = rng.integers(-9999, 9999, (2, 3, 5, 62, 400)).astype(dtype)
+        got = ssw.materialize_windows(clips)
+        assert np.array_equal(got, oracle.seg_sliding_window(clips, 0.5, 0.25))
+
+
+# ---- the fused path from raw recordings --------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def subject():
+    raw = synth.synth_subject(1, device=DEV)
+    return raw, raw.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode,win,hop,nwin", (("500ms", 100, 50, 7), ("1s", 200, 200, 2), ("2s", 400, 0, 1)))
+def test_fused_from_raw_full_subject(subject, mode, win, hop, nwin):
+    """One full-size subject (7 x 62 x 104000): every one of the 86 800 * nwin channel-windows against the
+    float64 closed form of the reference arithmetic."""
+    raw, raw_np = subject
+    de, psd = frontend.de_psd_from_raw(raw, mode)
+    want_shape = (7, 40, 5) + ((nwin,) if nwin > 1 else ()) + (62, 5)
+    assert tuple(de.shape) == want_shape and de.dtype == torch.float32
+    clips = oracle.segment_subject(raw_np)                                         # (7,40,5,62,400)
+    if nwin > 1:
+        wins = np.stack([clips[..., w * hop:w * hop + win] for w in range(nwin)], axis=3)   # (7,40,5,W,62,win)
+    else:
+        wins = clips
+    de_ref, psd_ref = oracle.de_psd_closed_form(wins, 200, TW[win])
+    assert_features_close(de.cpu().numpy(), psd.cpu().numpy(), de_ref, psd_ref)
+
+
+def test_fused_equals_staged_bit_for_bit(subject):
+    """raw -> features  ==  raw -> segment_clips -> features  ==  raw -> clips -> sliding windows -> features."""
+    raw, _ = subject
+    blocks = raw[:2]
+    de, psd = frontend.de_psd_from_raw(blocks, "500ms")
+    clips = frontend.segment_clips(blocks)
+    de_c, psd_c = frontend.de_psd_from_clips(clips, "500ms")
+    assert torch.equal(de, de_c) and torch.equal(psd, psd_c)
+    wins = frontend.sliding_windows(clips)
+    de_w, psd_w = frontend.de_psd_windows(wins)
+    assert torch.equal(de, de_w) and torch.equal(psd, psd_w)
+    for mode in ("1s", "2s"):
+        a = frontend.de_psd_from_raw(blocks, mode)
+        b = frontend.de_psd_from_clips(clips, mode)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_fused_against_loop_oracle_sample(subject):
+    """A random sample of clips against the loop-for-loop port of the reference (scipy.fftpack, math.log)."""
+    raw, raw_np = subject
+    de, psd = frontend.de_psd_from_raw(raw, "500ms")
+    de, psd = de.cpu().numpy(), psd.cpu().numpy()
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        b, c, r, w = rng.integers(7), rng.integers(40), rng.integers(5), rng.integers(7)
+        clip = oracle.extract_2s_segment(block=int(b), concept=int(c), repetition=int(r), data=raw_np)
+        de_ref, psd_ref = oracle.de_psd_loop(clip[:, 50 * w:50 * w + 100], 200, 0.5)
+        assert_features_close(de[b, c, r, w], psd[b, c, r, w], de_ref, psd_ref)
+
+
+def test_properties_at_full_size(subject):
+    """Size-independent properties on a full subject: exact x4 under x2 scaling, channel-permutation
+    equivariance, independence of the 2 s features from the clip's second half, determinism."""
+    raw, _ = subject
+    de, psd = frontend.de_psd_from_raw(raw, "500ms")
+    de2, psd2 = frontend.de_psd_from_raw(raw * 2, "500ms")
+    assert torch.equal(psd2, psd * 4)
+    assert torch.allclose(de2, de + 2, atol=2e-6)
+    perm = torch.randperm(62, device=DEV)
+    de_p, psd_p = frontend.de_psd_from_raw(raw[:, perm], "500ms")
+    assert torch.equal(psd_p, psd[..., perm, :]) and torch.equal(de_p, de[..., perm, :])
+    again = frontend.de_psd_from_raw(raw, "500ms")
+    assert torch.equal(again[0], de) and torch.equal(again[1], psd)
+    clips = frontend.segment_clips(raw[:1])
+    a = frontend.de_psd_from_clips(clips, "2s")
+    clips[..., 200:] = 1e6
+    b = frontend.de_psd_from_clips(clips, "2s")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_leading_axes_and_odd_channel_counts():
+    raw = synth.synth_blocks(3, 77, device=DEV, channels=5)
+    de, psd = frontend.de_psd_from_raw(raw.reshape(1, 3, 5, -1), "1s")
+    assert tuple(de.shape) == (1, 3, 40, 5, 2, 5, 5)
+    clips = oracle.segment_subject(np.concatenate([raw.cpu().numpy()] + [np.zeros((4, 5, 104000), np.float32)]))[:3]
+    wins = np.stack([clips[..., :200], clips[..., 200:]], axis=3)
+    de_ref, psd_ref = oracle.de_psd_closed_form(wins, 200, 1)
+    assert_features_close(de[0].cpu().numpy(), psd[0].cpu().numpy(), de_ref, psd_ref)
+
+
+def test_unaligned_block_length_uses_fallback_loader():
+    """T = 104001: rows are only 4-byte aligned, so TMA bulk copies are impossible; same results required."""
+    raw = synth.synth_blocks(1, 5, device=DEV, channels=62, block_len=104001)
+    de, psd = frontend.de_psd_from_raw(raw, "500ms")
+    aligned = raw[..., :104000].contiguous()
+    de_a, psd_a = frontend.de_psd_from_raw(aligned, "500ms")
+    assert torch.equal(de, de_a) and torch.equal(psd, psd_a)
