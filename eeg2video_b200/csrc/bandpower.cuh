@@ -17,8 +17,8 @@
 //   samples, the rest is zero padding and is never touched (NI = 4).  1 s / 2 s windows use all eight (NI = 8).
 // * The Hann weights are compile-time immediates; bins 99 and 100 are never formed.
 //
-// Cost per window (scalar-equivalent fp32 operations): ~2.45 k for NI = 4, ~2.8 k for NI = 8, against
-// ~7.6 k for a textbook 200-point complex FFT.  Everything is unrolled at compile time; all table look-ups
+// Cost per window (fp32 lane-operations): ~2.45 k for NI = 4, ~2.6 k for NI = 8, against ~7.6 k for a textbook
+// 200-point complex FFT.  Everything is unrolled at compile time; all table look-ups
 // below are constant expressions.
 #pragma once
 #include <type_traits>
@@ -67,13 +67,19 @@ constexpr int w8_re_code(int d) { constexpr int t[8] = {1, 2, 0, -2, -1, -2, 0, 
 constexpr int w8_im_code(int d) { constexpr int t[8] = {0, -2, -1, -2, 0, 2, 1, 2}; return t[d & 7]; }
 
 // ---- window samples ------------------------------------------------------------------------------------------
-// The window start is 8-byte aligned (offsets are multiples of 50 floats); samples are fetched as float2 pairs
-// (LDS.64 on the device; identical addresses are merged by the compiler).
-template <int N>
+// Samples are fetched as aligned vectors (identical addresses are merged by the compiler):
+//   VEC = 2: float2 / LDS.64 -- sliding 500 ms windows start at multiples of 50 floats, i.e. only 8-byte aligned;
+//   VEC = 4: float4 / LDS.128 -- 1 s / 2 s / pre-cut windows start 16-byte aligned.
+template <int N, int VEC>
 EEGFE_FN float sample(const float* win)
 {
-  const float2 p = *reinterpret_cast<const float2*>(win + (N & ~1));
-  return (N & 1) ? p.y : p.x;
+  if constexpr (VEC == 4) {
+    const float4 p = *reinterpret_cast<const float4*>(win + (N & ~3));
+    return (N & 3) == 0 ? p.x : (N & 3) == 1 ? p.y : (N & 3) == 2 ? p.z : p.w;
+  } else {
+    const float2 p = *reinterpret_cast<const float2*>(win + (N & ~1));
+    return (N & 1) ? p.y : p.x;
+  }
 }
 
 // ---- radix-5 butterfly (forward, w5 = exp(-2 pi i / 5)), in place ---------------------------------------------
@@ -112,77 +118,76 @@ EEGFE_FN void dft25(cf (&v)[25])
 }
 
 // ---- band accumulation -----------------------------------------------------------------------------------------
+// A band accumulator is a complex register holding (sum re^2, sum im^2): one packed FMA per bin and band.
 template <int BIN>
-EEGFE_FN void add_to_bands(float (&e)[5], float p)
+EEGFE_FN void add_power_to_bands(cf (&acc)[5], cf v)
 {
   static_for<0, 5>([&](auto b_) {
     constexpr int b = decltype(b_)::value;
-    if constexpr (in_band(b, BIN)) e[b] = f_add(e[b], p);
+    if constexpr (in_band(b, BIN)) acc[b] = c_fma_sq(v, acc[b]);
   });
 }
 
 // all 25 outputs of harmonic K1 in {1,2,3}: bins K (< 100) or their mirrors 200 - K
 template <int K1>
-EEGFE_FN void accumulate_complex(const cf (&v)[25], float (&e)[5])
+EEGFE_FN void accumulate_complex(const cf (&v)[25], cf (&acc)[5])
 {
   static_for<0, 25>([&](auto k2_) {
     constexpr int k2 = decltype(k2_)::value;
     constexpr int bin = fold_bin(bin_of(K1, k2));
-    if constexpr (bin <= 98) add_to_bands<bin>(e, c_norm2(v[dft25_slot(k2)]));
+    if constexpr (bin <= 98) add_power_to_bands<bin>(acc, v[dft25_slot(k2)]);
   });
 }
 
 // Z = DFT25(B_0 + i B_4):  2 A[k2] = Z[k2] + conj Z[-k2],  2i G[k2] = Z[k2] - conj Z[-k2].
-// Energies are accumulated unscaled into e4[] (the caller applies the exact factor 1/4).
-EEGFE_FN void accumulate_real_pair(const cf (&v)[25], float (&e4)[5])
+// Powers are accumulated unscaled (the caller applies the exact factor 1/4).
+EEGFE_FN void accumulate_real_pair(const cf (&v)[25], cf (&acc4)[5])
 {
   static_for<0, 13>([&](auto k2_) {
     constexpr int k2 = decltype(k2_)::value;
     const cf p = v[dft25_slot(k2)], q = v[dft25_slot((25 - k2) % 25)];
     constexpr int bin_a = fold_bin(bin_of(0, k2));
     constexpr int bin_g = fold_bin(bin_of(4, k2));
-    if constexpr (bin_a <= 98) add_to_bands<bin_a>(e4, c_norm2(c_add_conj(p, q)));
-    if constexpr (bin_g <= 98) add_to_bands<bin_g>(e4, c_norm2(c_sub_conj(p, q)));
+    if constexpr (bin_a <= 98) add_power_to_bands<bin_a>(acc4, c_add_conj(p, q));
+    if constexpr (bin_g <= 98) add_power_to_bands<bin_g>(acc4, c_sub_conj(p, q));
   });
 }
 
 // ---- radix-8 stage, 100-sample windows (four live inputs per group) ---------------------------------------------
 // Group RHO holds samples RHO + 25 i, i = 0..3, sitting at n1 = (J + i) mod 8 with J = rot_of_rho(RHO).
-template <int HANN, int RHO>
+// With y_i = x_i h_i (Hann weight h_i a compile-time immediate) every pair sum / difference is one multiply and
+// one FMA:  y_p + y_q = fma(x_q, h_q, x_p h_p),  y_p - y_q = fma(x_q, -h_q, x_p h_p).
+template <int HANN, int RHO, int VEC>
 struct Group4 {
   static constexpr int J = rot_of_rho(RHO);
   static constexpr int N2 = n2_of_rho(RHO);
   // signs that make B_2 = (-i)^J (d02 - i d13) come out without negations: u = SU (y0 - y2), v = SV (y1 - y3)
   static constexpr int SU = (J % 4 == 0 || J % 4 == 3) ? 1 : -1;
   static constexpr int SV = (J % 4 == 2 || J % 4 == 3) ? 1 : -1;
-  float y0, y1, y2, y3;
+  static constexpr float H0 = hann_at<HANN, RHO>(), H1 = hann_at<HANN, RHO + 25>();
+  static constexpr float H2 = hann_at<HANN, RHO + 50>(), H3 = hann_at<HANN, RHO + 75>();
+  float x0, x1, x2, x3;
 
   EEGFE_FN explicit Group4(const float* win)
-  {
-    constexpr float h0 = hann_at<HANN, RHO>(), h1 = hann_at<HANN, RHO + 25>();
-    constexpr float h2 = hann_at<HANN, RHO + 50>(), h3 = hann_at<HANN, RHO + 75>();
-    y0 = f_mul(sample<RHO>(win), h0);
-    y1 = f_mul(sample<RHO + 25>(win), h1);
-    y2 = f_mul(sample<RHO + 50>(win), h2);
-    y3 = f_mul(sample<RHO + 75>(win), h3);
-  }
-  EEGFE_FN float s02() const { return f_add(y0, y2); }
-  EEGFE_FN float s13() const { return f_add(y1, y3); }
-  EEGFE_FN float u() const { return SU > 0 ? f_sub(y0, y2) : f_sub(y2, y0); }
-  EEGFE_FN float v() const { return SV > 0 ? f_sub(y1, y3) : f_sub(y3, y1); }
+      : x0(sample<RHO, VEC>(win)), x1(sample<RHO + 25, VEC>(win)), x2(sample<RHO + 50, VEC>(win)),
+        x3(sample<RHO + 75, VEC>(win)) {}
 
-  // (B_0, B_4) packed as one complex number
-  EEGFE_FN cf even_pair() const
+  // (B_0, B_4) and B_2: the even sweep
+  EEGFE_FN void even(cf& b04, cf& b2) const
   {
-    const float a = s02(), b = s13();
-    return c_make(f_add(a, b), (J % 2 == 0) ? f_sub(a, b) : f_sub(b, a));
+    constexpr float h0 = H0, h1 = H1, h2 = H2, h3 = H3;
+    const float t0 = f_mul(x0, h0), t1 = f_mul(x1, h1);
+    const float s02 = f_fma(x2, h2, t0), s13 = f_fma(x3, h3, t1);
+    const float u = SU > 0 ? f_fma(x2, -h2, t0) : f_fma(x2, h2, -t0);
+    const float v = SV > 0 ? f_fma(x3, -h3, t1) : f_fma(x3, h3, -t1);
+    b04 = c_make(f_add(s02, s13), (J % 2 == 0) ? f_sub(s02, s13) : f_sub(s13, s02));
+    b2 = (J % 2 == 0) ? c_make(u, v) : c_make(v, u);
   }
-  EEGFE_FN cf harmonic2() const { return (J % 2 == 0) ? c_make(u(), v()) : c_make(v(), u()); }
 
   // one component (IM = 0: real part, 1: imaginary part) of B_K1, K1 in {1, 3}:
   //   +-y_axis + (+-sqrt(1/2)) * (sum or signed difference of the diagonal pair)
   template <int K1, int IM>
-  EEGFE_FN float odd_component(float sp, float ep) const   // sp / ep: sum / signed difference of the diagonal pair
+  EEGFE_FN float odd_component(float sp, float ep, float ya0, float ya1) const
   {
     constexpr int code0 = IM ? w8_im_code((J + 0) * K1) : w8_re_code((J + 0) * K1);
     constexpr int code1 = IM ? w8_im_code((J + 1) * K1) : w8_re_code((J + 1) * K1);
@@ -193,104 +198,142 @@ struct Group4 {
     constexpr int ax = diag_is_02 ? code1 : code0, ax2 = diag_is_02 ? code3 : code2;      // one is +-1, other 0
     static_assert((dq == 2 || dq == -2) && (dq2 == 2 || dq2 == -2), "diagonal pair");
     static_assert((ax == 0) != (ax2 == 0), "axis pair");
-    const float ya = diag_is_02 ? (ax != 0 ? y1 : y3) : (ax != 0 ? y0 : y2);
+    const float ya = (ax != 0) ? ya0 : ya1;              // ya0 / ya1: first / second member of the axis pair
     constexpr int sa = (ax != 0) ? ax : ax2;
-    constexpr int se = diag_is_02 ? SU : SV;                                              // sign carried by ep
+    constexpr int se = diag_is_02 ? SU : SV;             // sign carried by ep
     constexpr float kappa = (dq == dq2) ? (dq > 0 ? tab::kRh : -tab::kRh)
                                         : ((dq > 0) == (se > 0) ? tab::kRh : -tab::kRh);
     return f_fma(kappa, (dq == dq2) ? sp : ep, sa > 0 ? ya : -ya);
   }
-  template <int K1>
-  EEGFE_FN cf harmonic_odd() const
+
+  // B_1 and B_3: the odd sweep
+  EEGFE_FN void odd(cf& b1, cf& b3) const
   {
-    const float sp = (J % 2 != 0) ? s02() : s13();
-    const float ep = (J % 2 != 0) ? u() : v();
-    return c_make(odd_component<K1, 0>(sp, ep), odd_component<K1, 1>(sp, ep));
+    constexpr float h0 = H0, h1 = H1, h2 = H2, h3 = H3;
+    float sp, ep, ya0, ya1;
+    if constexpr (J % 2 != 0) {          // diagonal pair (0, 2), axis pair (1, 3)
+      const float t = f_mul(x0, h0);
+      sp = f_fma(x2, h2, t);
+      ep = SU > 0 ? f_fma(x2, -h2, t) : f_fma(x2, h2, -t);
+      ya0 = f_mul(x1, h1);
+      ya1 = f_mul(x3, h3);
+    } else {                             // diagonal pair (1, 3), axis pair (0, 2)
+      const float t = f_mul(x1, h1);
+      sp = f_fma(x3, h3, t);
+      ep = SV > 0 ? f_fma(x3, -h3, t) : f_fma(x3, h3, -t);
+      ya0 = f_mul(x0, h0);
+      ya1 = f_mul(x2, h2);
+    }
+    b1 = c_make(odd_component<1, 0>(sp, ep, ya0, ya1), odd_component<1, 1>(sp, ep, ya0, ya1));
+    b3 = c_make(odd_component<3, 0>(sp, ep, ya0, ya1), odd_component<3, 1>(sp, ep, ya0, ya1));
   }
 };
 
 // ---- radix-8 stage, 200-sample windows (all eight inputs) --------------------------------------------------------
-template <int HANN, int RHO>
+// z_n = windowed sample sitting at n1 = n.  The even sweep only needs the sums z_n + z_{n+4}, the odd sweep only
+// the differences z_n - z_{n+4}: one multiply and one FMA each.
+template <int HANN, int RHO, int VEC>
 struct Group8 {
   static constexpr int J = rot_of_rho(RHO);
   static constexpr int N2 = n2_of_rho(RHO);
-  float sa, da, sb, db, sc, dc, sd, dd;       // sums / differences of (z_n, z_{n+4}), z indexed by n1
+  const float* win;
+  EEGFE_FN explicit Group8(const float* w) : win(w) {}
 
   template <int N1>
-  EEGFE_FN static float z(const float* win)   // windowed sample sitting at n1 = N1
+  static constexpr int input_of() { return (N1 - J + 8) % 8; }           // which of the 8 samples sits at n1 = N1
+  template <int N1, int SIGN>
+  EEGFE_FN float pair() const                                             // z_{N1} + SIGN * z_{N1 + 4}
   {
-    constexpr int i = (N1 - J + 8) % 8;
-    constexpr float h = hann_at<HANN, RHO + 25 * i>();
-    return f_mul(sample<RHO + 25 * i>(win), h);
+    constexpr int ia = input_of<N1>(), ib = input_of<N1 + 4>();
+    constexpr float ha = hann_at<HANN, RHO + 25 * ia>(), hb = hann_at<HANN, RHO + 25 * ib>();
+    const float t = f_mul(sample<RHO + 25 * ia, VEC>(win), ha);
+    return f_fma(sample<RHO + 25 * ib, VEC>(win), SIGN > 0 ? hb : -hb, t);
   }
-  EEGFE_FN explicit Group8(const float* win)
+  EEGFE_FN void even(cf& b04, cf& b2) const
   {
-    const float z0 = z<0>(win), z1 = z<1>(win), z2 = z<2>(win), z3 = z<3>(win);
-    const float z4 = z<4>(win), z5 = z<5>(win), z6 = z<6>(win), z7 = z<7>(win);
-    sa = f_add(z0, z4); da = f_sub(z0, z4);
-    sb = f_add(z1, z5); db = f_sub(z1, z5);
-    sc = f_add(z2, z6); dc = f_sub(z2, z6);
-    sd = f_add(z3, z7); dd = f_sub(z3, z7);
-  }
-  EEGFE_FN cf even_pair() const
-  {
+    const float sa = pair<0, 1>(), sb = pair<1, 1>(), sc = pair<2, 1>(), sd = pair<3, 1>();
     const float e = f_add(sa, sc), o = f_add(sb, sd);
-    return c_make(f_add(e, o), f_sub(e, o));
+    b04 = c_make(f_add(e, o), f_sub(e, o));
+    b2 = c_make(f_sub(sa, sc), f_sub(sd, sb));
   }
-  EEGFE_FN cf harmonic2() const { return c_make(f_sub(sa, sc), f_sub(sd, sb)); }
-  template <int K1>
-  EEGFE_FN cf harmonic_odd() const
+  EEGFE_FN void odd(cf& b1, cf& b3) const
   {
+    const float da = pair<0, -1>(), db = pair<1, -1>(), dc = pair<2, -1>(), dd = pair<3, -1>();
     const float p = f_sub(db, dd), q = f_add(db, dd);
-    if constexpr (K1 == 1) return c_make(f_fma(tab::kRh, p, da), f_fma(-tab::kRh, q, -dc));
-    else return c_make(f_fma(-tab::kRh, p, da), f_fma(-tab::kRh, q, dc));
+    b1 = c_make(f_fma(tab::kRh, p, da), f_fma(-tab::kRh, q, -dc));
+    b3 = c_make(f_fma(-tab::kRh, p, da), f_fma(-tab::kRh, q, dc));
   }
 };
 
-template <int NI, int HANN, int RHO>
-using Group = std::conditional_t<NI == 4, Group4<HANN, RHO>, Group8<HANN, RHO>>;
+template <int NI, int HANN, int RHO, int VEC>
+using Group = std::conditional_t<NI == 4, Group4<HANN, RHO, VEC>, Group8<HANN, RHO, VEC>>;
 
 // ---- one window -> unnormalised band energies E_b = sum_{k in band b} |X[k]|^2 ------------------------------------
 // NI = 4: `win` holds 100 samples (zero-padded transform);  NI = 8: `win` holds 200 samples.
-// Two sweeps over the window keep two DFT-25 work sets (100 registers) live at a time instead of four.
-template <int NI, int HANN>
+// The work is two independent sweeps over the window, each forming two radix-8 output sequences and running two
+// DFT-25 (100 registers of work set instead of 200):
+//   even sweep: harmonics k1 = 0, 4 (one shared DFT) and k1 = 2   -> part_even[b]
+//   odd  sweep: harmonics k1 = 1 and k1 = 3                        -> part_odd[b]
+//   E_b = part_even[b] + part_odd[b]
+// A thread may run both (500 ms kernel) or the two sweeps may run in different warps (1 s / 2 s kernels); the
+// partial sums and their final addition are identical either way, so all paths agree bit for bit.
+template <int NI, int HANN, int VEC>
+EEGFE_FN void sweep_even(const float* win, float (&part)[5])
+{
+  cf acc[5];
+  static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_make(0.f, 0.f); });
+  cf b04[25], b2[25];
+  static_for<0, 25>([&](auto rho_) {
+    constexpr int rho = decltype(rho_)::value;
+    const Group<NI, HANN, rho, VEC> g(win);
+    g.even(b04[g.N2], b2[g.N2]);
+  });
+  dft25(b04);
+  accumulate_real_pair(b04, acc);
+  static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_mul_s(acc[decltype(b_)::value], 0.25f); });
+  dft25(b2);
+  accumulate_complex<2>(b2, acc);
+  static_for<0, 5>([&](auto b_) {
+    constexpr int b = decltype(b_)::value;
+    part[b] = f_add(c_re(acc[b]), c_im(acc[b]));
+  });
+}
+
+template <int NI, int HANN, int VEC>
+EEGFE_FN void sweep_odd(const float* win, float (&part)[5])
+{
+  cf acc[5];
+  static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_make(0.f, 0.f); });
+  cf b1[25], b3[25];
+  static_for<0, 25>([&](auto rho_) {
+    constexpr int rho = decltype(rho_)::value;
+    const Group<NI, HANN, rho, VEC> g(win);
+    g.odd(b1[g.N2], b3[g.N2]);
+  });
+  dft25(b1);
+  accumulate_complex<1>(b1, acc);
+  dft25(b3);
+  accumulate_complex<3>(b3, acc);
+  static_for<0, 5>([&](auto b_) {
+    constexpr int b = decltype(b_)::value;
+    part[b] = f_add(c_re(acc[b]), c_im(acc[b]));
+  });
+}
+
+template <int NI, int HANN, int VEC>
 EEGFE_FN void window_band_energy(const float* win, float (&energy)[5])
 {
-  float e[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, e4[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  {
-    cf b04[25], b2[25];
-    static_for<0, 25>([&](auto rho_) {
-      constexpr int rho = decltype(rho_)::value;
-      const Group<NI, HANN, rho> g(win);
-      b04[g.N2] = g.even_pair();
-      b2[g.N2] = g.harmonic2();
-    });
-    dft25(b04);
-    accumulate_real_pair(b04, e4);
-    dft25(b2);
-    accumulate_complex<2>(b2, e);
-  }
+  float pe[5], po[5];
+  sweep_even<NI, HANN, VEC>(win, pe);
   // Without this the compiler (nvcc AND ptxas) merges the sample loads and the radix-8 partial sums of the two
   // sweeps and keeps ~100 extra values live across the first pair of DFTs -- exactly what the two sweeps are
   // there to avoid.  The second sweep therefore reads through a pointer offset by a run-time zero.
   asm volatile("" ::: "memory");
   win += EEGFE_OPAQUE_ZERO();
-  {
-    cf b1[25], b3[25];
-    static_for<0, 25>([&](auto rho_) {
-      constexpr int rho = decltype(rho_)::value;
-      const Group<NI, HANN, rho> g(win);
-      b1[g.N2] = g.template harmonic_odd<1>();
-      b3[g.N2] = g.template harmonic_odd<3>();
-    });
-    dft25(b1);
-    accumulate_complex<1>(b1, e);
-    dft25(b3);
-    accumulate_complex<3>(b3, e);
-  }
+  sweep_odd<NI, HANN, VEC>(win, po);
   static_for<0, 5>([&](auto b_) {
     constexpr int b = decltype(b_)::value;
-    energy[b] = f_fma(0.25f, e4[b], e[b]);
+    energy[b] = f_add(pe[b], po[b]);
   });
 }
 

@@ -64,6 +64,7 @@ EEGFE_FN cf c_mul_w(cf a, float wr, float wi)                                   
   u64_ t = mul2_(a.v, pk_(wr, wr));
   return cf{fma2_(swp_(a.v), pk_(-wi, wi), t)};
 }
+EEGFE_FN cf c_fma_sq(cf a, cf c) { return cf{fma2_(a.v, a.v, c.v)}; }                         // (re^2, im^2) + c
 #else
 // ---- scalar backend ------------------------------------------------------------------------------------------
 struct cf { float re, im; };
@@ -83,8 +84,7 @@ EEGFE_FN cf c_mul_w(cf a, float wr, float wi)
   float tr = f_mul(a.re, wr), ti = f_mul(a.im, wr);
   return cf{f_fma(a.im, -wi, tr), f_fma(a.re, wi, ti)};
 }
+EEGFE_FN cf c_fma_sq(cf a, cf c) { return cf{f_fma(a.re, a.re, c.re), f_fma(a.im, a.im, c.im)}; }
 #endif
-
-EEGFE_FN float c_norm2(cf a) { float r = c_re(a), i = c_im(a); return f_fma(i, i, f_mul(r, r)); }   // |a|^2
 
 }  // namespace eegfe

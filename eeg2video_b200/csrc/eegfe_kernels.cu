@@ -26,17 +26,18 @@ struct Job {
   float* de;
   float* psd;
   int* status;
-  long long total_rows;   // n_units * n_ch
+  unsigned total_rows;    // n_units * n_ch of THIS launch (< 2^31; the host splits larger jobs)
   long long base;         // element offset of unit u: base + (u / d1) * s0 + ((u % d1) / d2) * s1 + (u % d2) * s2
-  long long s0, s1, s2;
+  long long s0;
+  int s1, s2;
   long long ch_stride;    // elements between channel rows of one unit
-  int d1, d2;
-  int n_ch;
-  int aligned16;          // every row start is 16-byte aligned -> TMA bulk copies; else cooperative loads
+  unsigned d1, d2;
+  unsigned n_ch;
 };
 
 // per-mode compile-time geometry
-template <int LOAD_, int NWIN_, int HOP_, int NI_, int HANN_, int ROWS_, int NBUF_, int CTAS_>
+template <int LOAD_, int NWIN_, int HOP_, int NI_, int HANN_, int ROWS_, int GROUPS_, int SLOTS_, int CTAS_, int PAD_,
+          int VEC_, int SPLIT_, bool LANEMAP_, bool GSTORE_>
 struct Cfg {
   static constexpr int kLoad = LOAD_;        // samples fetched per row
   static constexpr int kWindows = NWIN_;     // analysis windows per row
@@ -44,19 +45,51 @@ struct Cfg {
   static constexpr int kNi = NI_;            // live inputs per radix-8 group (4: 100-sample window, 8: 200)
   static constexpr int kHann = HANN_;
   static constexpr int kRows = ROWS_;        // rows per tile
-  static constexpr int kBufs = NBUF_;        // shared-memory stages
+  static constexpr int kGroups = GROUPS_;    // worker groups per CTA; group g owns the CTA's tiles g, g + G, ...
+  static constexpr int kSlots = SLOTS_;      // input ring slots per CTA (> kGroups: the surplus is prefetch depth)
   static constexpr int kCtasPerSm = CTAS_;
+  static constexpr int kRowStride = LOAD_ + PAD_;              // floats between rows in shared memory (bank skew)
+  static constexpr int kVec = VEC_;          // floats per shared-memory load (2: LDS.64, 4: LDS.128)
+  static constexpr int kSplit = SPLIT_;      // threads per channel-window (2: even / odd sweep in different warps)
+  static constexpr bool kLaneMap = LANEMAP_; // thread -> (row, window) through c_lane_map_500
+  static constexpr bool kGroupStore = GSTORE_;  // features are written out by the group itself, not the producer warp
   static constexpr int kUnits = ROWS_ * NWIN_;                 // channel-windows per tile
-  static constexpr int kThreads = (kUnits + 31) / 32 * 32;
+  static constexpr int kGroupThreads = kUnits * SPLIT_;        // worker threads per group
+  static constexpr int kGroupWarps = kGroupThreads / 32;
+  static constexpr int kWorkers = kGroupThreads * GROUPS_;
+  static constexpr int kThreads = kWorkers + 32;               // + one producer / storer warp
   static constexpr int kRowBytes = LOAD_ * 4;
-  static constexpr int kSmemBytes = NBUF_ * ROWS_ * LOAD_ * 4;
+  static constexpr int kSlotFloats = ROWS_ * kRowStride;
+  static constexpr int kOutFloats = kUnits * 5;                // per staging array, laid out [row][window][band]
+  static constexpr int kMeta = 2 * SLOTS_;   // tile-geometry ring: a tile's entry must outlive its input slot (see kernel)
+  static constexpr int kSmemBytes = (SLOTS_ * kSlotFloats + GROUPS_ * 2 * kOutFloats) * 4 + kMeta * (ROWS_ + 1) * 4;
+  static_assert(kUnits % 32 == 0, "a tile must fill whole warps");
+  static_assert(kRowBytes % 16 == 0 && kRowStride % 4 == 0, "TMA bulk copies need 16-byte aligned rows");
+  static_assert(SPLIT_ == 1 || SPLIT_ == 2, "one or two threads per channel-window");
+  static_assert(SPLIT_ == 1 || GSTORE_, "split sweeps are combined by the group");
+  static_assert(GROUPS_ <= 15, "one named barrier per group");
+  static_assert(SLOTS_ >= 2 * GROUPS_, "geometry ring safety: tile m is written out before tile m + 2 kSlots is loaded");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
-//                         LOAD NWIN HOP NI  HANN          ROWS NBUF CTAS
-using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 2, 2>;    // 224 threads, 100 KB smem
-using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 32, 2, 2>;    //  64 threads
-using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 64, 2, 2>;      //  64 threads (only samples 0..199 are read)
-using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 128, 2, 2>;    // 128 threads, pre-cut 500 ms windows
-using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 64, 2, 2>;      //  64 threads, pre-cut 1 s windows
+// Shared-memory bank rules behind PAD / VEC (B200: 32 banks x 4 B; 64-bit loads are served per half-warp,
+// 128-bit loads per quarter-warp):
+//  * sliding 500 ms: windows start every 50 floats (8-byte aligned) -> LDS.64; stride 404 + the lane map of
+//    eegfe_tables.h gives 16 wavefronts per load step (14 ideal, 28 with dense rows and thread = 7 row + window);
+//  * 1 s / 2 s / pre-cut: windows start 16-byte aligned -> LDS.128 with lanes = consecutive rows, conflict-free
+//    iff (row stride / 4) is odd: 404 -> 101, 204 -> 51, 100 -> 25.
+// Ring sizing: the 500 ms kernel is FP32-bound (one tile of prefetch per group is plenty) and its 224-thread group
+// leaves the producer warp time to double as the storer.  The 1 s / 2 s / pre-cut kernels are HBM-bound at 800 B
+// (400 B) per channel-window and want ~100 KB per SM in flight, hence small tiles, four groups and as many surplus
+// slots as shared memory holds; a tile is due every ~1 us per SM there, too fast for one warp to also write the
+// features, so each group stores its own tile (kGroupStore) and the producer only issues copies.
+//                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP GSTORE
+using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, false>;   // 224 + 32 thr, 110 KB x 2
+using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 4, 8, 1, 4, 4, 2, false, true>;   // 4 x 64 + 32 thr, 212 KB
+using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, true>;     // 4 x 64 + 32 (samples 0..199)
+using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, true>;    // 4 x 64 + 32, pre-cut 500 ms
+using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 4, 8, 1, 4, 4, 2, false, true>;     // 4 x 64 + 32, pre-cut 1 s
+
+__constant__ unsigned char c_lane_map_500[224] = {EEGFE_LANE_MAP_500};
 
 // ---------------------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy helpers (PTX)
@@ -71,6 +104,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
   uint32_t done;
@@ -84,6 +121,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)     // non-blocking phase test
+{
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -92,105 +141,296 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                : "memory");
 }
 
-__device__ __forceinline__ long long row_offset(const Job& job, long long g)
+// row g (32-bit) -> element offset of its first sample, and the index of its first output value
+__device__ __forceinline__ long long row_offset(const Job& job, unsigned g, int n_windows, int* out_base)
 {
-  const long long u = g / job.n_ch;
-  const int ch = static_cast<int>(g - u * job.n_ch);
-  const long long q = u / job.d1;
-  const int rem = static_cast<int>(u - q * job.d1);
-  return job.base + q * job.s0 + (rem / job.d2) * job.s1 + (rem % job.d2) * job.s2 + ch * job.ch_stride;
+  const unsigned u = g / job.n_ch;
+  const unsigned ch = g - u * job.n_ch;
+  const unsigned q = u / job.d1;
+  const unsigned rem = u - q * job.d1;
+  const unsigned c = rem / job.d2;
+  const unsigned r = rem - c * job.d2;
+  if (out_base) *out_base = static_cast<int>((u * n_windows * job.n_ch + ch) * 5u);
+  return job.base + static_cast<long long>(q) * job.s0 + static_cast<int>(c) * job.s1 + static_cast<int>(r) * job.s2 +
+         static_cast<long long>(ch) * job.ch_stride;
 }
 
-// E_b -> psd_b = E_b / count_b (DE_PSD.py:66), de_b = log2(100 psd_b) (:68); counts 4, 5, 7, 18, 69
-__device__ __forceinline__ void store_features(const Job& job, long long g, int w, int n_windows, const float (&e)[5])
+// E_b -> psd_b = E_b / count_b (DE_PSD.py:66), de_b = log2(100 psd_b) (:68); counts 4, 5, 7, 18, 69.
+// The reciprocal multiply and MUFU.LG2 are each good to ~1 ulp (1e-7 relative / 4e-6 absolute at DE ~ 20),
+// two orders inside the parity bars.
+__device__ __forceinline__ float inv_count(int b)
 {
-  const long long u = g / job.n_ch;
-  const int ch = static_cast<int>(g - u * job.n_ch);
-  const long long o = ((u * n_windows + w) * job.n_ch + ch) * 5;
-  const float cnt[5] = {4.0f, 5.0f, 7.0f, 18.0f, 69.0f};
+  return b == 0 ? 1.0f / 4.0f : b == 1 ? 1.0f / 5.0f : b == 2 ? 1.0f / 7.0f : b == 3 ? 1.0f / 18.0f : 1.0f / 69.0f;
+}
+__device__ __forceinline__ bool band_features(const float (&e)[5], float (&psd)[5], float (&de)[5])
+{
   bool zero = false;
 #pragma unroll
   for (int b = 0; b < 5; ++b) {
-    const float p = __fdiv_rn(e[b], cnt[b]);
-    zero |= (p == 0.0f);
-    job.psd[o + b] = p;
-    job.de[o + b] = log2f(__fmul_rn(100.0f, p));
+    psd[b] = e[b] * inv_count(b);
+    zero |= (psd[b] == 0.0f);
+    de[b] = __log2f(100.0f * psd[b]);
   }
-  if (zero && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
+  return zero;
+}
+
+// Write one staged tile to HBM.  Thread `t` of `nthreads` takes consecutive (row, band) of one window, i.e.
+// consecutive addresses while the rows stay inside a clip.  kSplit == 2: the two sweeps' partials are added and
+// turned into (psd, de) here.  Returns true if a zero-power band was seen (kSplit == 2 only).
+template <class C>
+__device__ __forceinline__ bool store_tile(const Job& job, const float* out_a, const float* out_b, const int* rbase,
+                                           int nrows, int t, int nthreads)
+{
+  const int win_stride = static_cast<int>(job.n_ch) * 5;
+  bool zero = false;
+#pragma unroll 4
+  for (int j = t; j < C::kOutFloats; j += nthreads) {
+    const int w = j / (C::kRows * 5);
+    const int rem = j - w * (C::kRows * 5);
+    const int r = rem / 5;
+    const int b = rem - r * 5;
+    if (r < nrows) {
+      const int e = (r * C::kWindows + w) * 5 + b;
+      const int o = rbase[r] + w * win_stride + b;
+      if constexpr (C::kSplit == 1) {
+        job.de[o] = out_a[e];
+        job.psd[o] = out_b[e];
+      } else {
+        const float p = __fadd_rn(out_a[e], out_b[e]) * inv_count(b);
+        zero |= (p == 0.0f);
+        job.psd[o] = p;
+        job.de[o] = __log2f(100.0f * p);
+      }
+    }
+  }
+  return zero;
+}
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// worker-local unit index -> (row in tile, window)
+template <class C>
+__device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
+{
+  if constexpr (C::kLaneMap) {
+    const int code = c_lane_map_500[unit];
+    row = code >> 3;
+    w = code & 7;
+  } else if constexpr (C::kWindows == 1) {
+    row = unit;
+    w = 0;
+  } else {                       // lanes run over consecutive rows, the window is warp-uniform
+    w = unit / C::kRows;
+    row = unit - w * C::kRows;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// the fused kernel
+// the fused kernel (rows 16-byte aligned): warp-specialised, no block-wide barrier in the steady state
+//
+// A CTA walks its tiles m = 0, 1, 2, ... (global tile blockIdx.x + m * gridDim.x).  Tile m lands in ring slot
+// m % kSlots and is processed by worker group m % kGroups.
+//
+//   producer warp : for m = 0, 1, ...   wait empty[slot] -> row geometry + one TMA bulk copy per row -> full[slot]
+//                   then (storer role)  wait out_full[g] of tile m - kGroups -> coalesced copy of its features
+//                                       to HBM -> out_empty[g]
+//   worker group g: for its tiles       wait full[slot] -> one channel-window (or one of its two sweeps) per
+//                                       thread, register FFT -> arrive empty[slot]
+//                                       wait out_empty[g] -> staging tile [row][window][band] -> arrive out_full[g]
+//
+// kSplit == 1: a worker runs both sweeps and the epilogue and stages (de, psd).
+// kSplit == 2: even-sweep warps and odd-sweep warps stage their partial band energies; the storer adds them
+//              and does the epilogue (the same additions, so the result is bit-identical to kSplit == 1).
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* const bufs = reinterpret_cast<float*>(smem_raw);
-  __shared__ uint64_t full_bar[C::kBufs];
+  float* const ring = reinterpret_cast<float*>(smem_raw);
+  float* const out_stage = ring + C::kSlots * C::kSlotFloats;               // [group][2][kOutFloats]
+  // Tile geometry (first output index per row, live rows) lives in a ring of 2 kSlots entries indexed by tile
+  // number: the loader may refill tile m's INPUT slot (tile m + kSlots) before the storer has written tile m out,
+  // but it cannot load tile m + 2 kSlots before that (needs tile m + kSlots consumed => its group staged tile
+  // m + kSlots - kGroups => the in-order storer drained tile m + kSlots - 2 kGroups >= m).
+  int* const row_base = reinterpret_cast<int*>(out_stage + C::kGroups * 2 * C::kOutFloats);   // [meta][row]
+  int* const tile_rows = row_base + C::kMeta * C::kRows;                    // [meta]: live rows of the tile
+  __shared__ uint64_t full_bar[C::kSlots], empty_bar[C::kSlots], out_full_bar[C::kGroups], out_empty_bar[C::kGroups];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const bool loader_warp = (tid < 32);
-  const long long n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
-  const int row_in_tile = tid / C::kWindows;
-  const int w = tid - row_in_tile * C::kWindows;
-  const bool has_unit = tid < C::kUnits;
+  const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int n_mine = blockIdx.x < n_tiles ? static_cast<int>((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
 
-  if (job.aligned16) {
-    if (tid == 0) {
+  if (tid == 0) {
 #pragma unroll
-      for (int b = 0; b < C::kBufs; ++b) mbar_init(&full_bar[b], 1);
-      mbar_fence_init();
+    for (int s = 0; s < C::kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], C::kGroupWarps);
     }
-    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < C::kGroups; ++g) {
+      mbar_init(&out_full_bar[g], C::kGroupWarps);
+      mbar_init(&out_empty_bar[g], 1);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
 
-    auto issue = [&](long long tile, int buf) {          // warp 0: one bulk copy per row of the tile
-      const long long row0 = tile * C::kRows;
-      const long long left = job.total_rows - row0;
-      const int nrows = left < C::kRows ? static_cast<int>(left) : C::kRows;
-      if (lane == 0) mbar_arrive_expect_tx(&full_bar[buf], static_cast<uint32_t>(nrows) * C::kRowBytes);
-      __syncwarp();
-      for (int r = lane; r < nrows; r += 32)
-        bulk_copy_g2s(bufs + (buf * C::kRows + r) * C::kLoad, job.in + row_offset(job, row0 + r), C::kRowBytes,
-                      &full_bar[buf]);
-    };
-
-    long long tile = blockIdx.x;
-    if (loader_warp && tile < n_tiles) issue(tile, 0);
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int buf = it % C::kBufs;
-      const long long next = tile + gridDim.x;
-      if (C::kBufs > 1 && loader_warp && next < n_tiles) issue(next, (it + 1) % C::kBufs);
-      mbar_wait(&full_bar[buf], (it / C::kBufs) & 1);
-      const long long g = tile * C::kRows + row_in_tile;
-      if (has_unit && g < job.total_rows) {
-        float e[5];
-        window_band_energy<C::kNi, C::kHann>(bufs + (buf * C::kRows + row_in_tile) * C::kLoad + w * C::kHop, e);
-        store_features(job, g, w, C::kWindows, e);
+  if (tid >= C::kWorkers) {
+    // ------------------------------------------------ producer / storer warp ------------------------------------
+    // Two cursors: loads run ahead as far as the ring has free slots; with !kGroupStore finished tiles are also
+    // written out here, in order, whenever their group has staged them.  Neither role ever blocks the other.
+    int next_load = 0, next_store = C::kGroupStore ? n_mine : 0;
+    while (next_load < n_mine || next_store < n_mine) {
+      bool progressed = false;
+      if (next_load < n_mine) {
+        const int m = next_load;
+        const int s = m % C::kSlots;
+        bool free_slot;
+        if constexpr (C::kGroupStore) {
+          mbar_wait(&empty_bar[s], ((m / C::kSlots) & 1) ^ 1);      // nothing else to do: block
+          free_slot = true;
+        } else {
+          free_slot = mbar_test(&empty_bar[s], ((m / C::kSlots) & 1) ^ 1);
+        }
+        if (free_slot) {
+          const unsigned row0 = (blockIdx.x + static_cast<unsigned>(m) * gridDim.x) * C::kRows;
+          const unsigned left = job.total_rows - row0;
+          const unsigned nrows = left < C::kRows ? left : C::kRows;
+          const int mi = m % C::kMeta;
+          if (lane == 0) {
+            tile_rows[mi] = static_cast<int>(nrows);
+            mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
+          }
+          __syncwarp();
+          for (unsigned r = lane; r < nrows; r += 32) {
+            int ob;
+            const long long off = row_offset(job, row0 + r, C::kWindows, &ob);
+            row_base[mi * C::kRows + r] = ob;
+            bulk_copy_g2s(ring + s * C::kSlotFloats + r * C::kRowStride, job.in + off, C::kRowBytes, &full_bar[s]);
+          }
+          __syncwarp();
+          ++next_load;
+          progressed = true;
+        }
       }
-      __syncthreads();                                   // everyone is done reading `buf`
-      if (C::kBufs == 1 && loader_warp && next < n_tiles) issue(next, 0);
+      if constexpr (!C::kGroupStore) {
+        if (next_store < next_load) {
+          const int mo = next_store;
+          const int g = mo % C::kGroups;
+          if (mbar_test(&out_full_bar[g], (mo / C::kGroups) & 1)) {
+            const int pm = mo % C::kMeta;
+            const float* const out_a = out_stage + g * 2 * C::kOutFloats;
+            store_tile<C>(job, out_a, out_a + C::kOutFloats, row_base + pm * C::kRows, tile_rows[pm], lane, 32);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&out_empty_bar[g]);
+            ++next_store;
+            progressed = true;
+          }
+        }
+        if (!progressed) __nanosleep(64);
+      }
     }
   } else {
-    // rows not 16-byte aligned (odd block lengths / strides): cooperative 4-byte loads, single stage
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long row0 = tile * C::kRows;
-      const long long left = job.total_rows - row0;
-      const int nrows = left < C::kRows ? static_cast<int>(left) : C::kRows;
-      for (int r = tid / 32; r < nrows; r += C::kThreads / 32) {
-        const float* src = job.in + row_offset(job, row0 + r);
-        for (int i = lane; i < C::kLoad; i += 32) bufs[r * C::kLoad + i] = __ldg(src + i);
+    // ------------------------------------------------ worker warps ----------------------------------------------
+    const int g = tid / C::kGroupThreads;
+    const int gt = tid - g * C::kGroupThreads;
+    const int sweep = gt / C::kUnits;                  // 0 when kSplit == 1; warp-uniform (kUnits % 32 == 0)
+    const int unit = gt - sweep * C::kUnits;
+    int row_in_tile, w;
+    unit_to_row_window<C>(unit, row_in_tile, w);
+    const int slot_out = (row_in_tile * C::kWindows + w) * 5;
+    float* const out_a = out_stage + g * 2 * C::kOutFloats;
+    float* const out_b = out_a + C::kOutFloats;
+    float* const out_mine = (C::kSplit == 2 && sweep == 1) ? out_b : out_a;
+    int j = 0;                                         // this group's j-th tile
+    for (int m = g; m < n_mine; m += C::kGroups, ++j) {
+      const int s = m % C::kSlots;
+      mbar_wait(&full_bar[s], (m / C::kSlots) & 1);
+      const bool live = row_in_tile < tile_rows[m % C::kMeta];
+      const float* win = ring + s * C::kSlotFloats + row_in_tile * C::kRowStride + w * C::kHop;
+      float va[5], vb[5];
+      if (live) {
+        if constexpr (C::kSplit == 1) {
+          float e[5];
+          window_band_energy<C::kNi, C::kHann, C::kVec>(win, e);
+          if (band_features(e, vb, va) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
+        } else if (sweep == 0) {
+          sweep_even<C::kNi, C::kHann, C::kVec>(win, va);
+        } else {
+          sweep_odd<C::kNi, C::kHann, C::kVec>(win, va);
+        }
       }
-      __syncthreads();
-      const long long g = row0 + row_in_tile;
-      if (has_unit && g < job.total_rows) {
-        float e[5];
-        window_band_energy<C::kNi, C::kHann>(bufs + row_in_tile * C::kLoad + w * C::kHop, e);
-        store_features(job, g, w, C::kWindows, e);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp no longer reads the input slot
+      if constexpr (C::kGroupStore) {
+        // staging tile is free again once every thread of the group finished storing the previous tile
+        if (j > 0) group_barrier(1 + g, C::kGroupThreads);
+      } else {
+        mbar_wait(&out_empty_bar[g], (j & 1) ^ 1);         // staging tile drained by the storer warp
       }
-      __syncthreads();
+      if (live) {
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+          out_mine[slot_out + b] = va[b];
+          if constexpr (C::kSplit == 1) out_b[slot_out + b] = vb[b];
+        }
+      }
+      if constexpr (C::kGroupStore) {
+        group_barrier(1 + g, C::kGroupThreads);            // all of the group's results are staged
+        const int pm = m % C::kMeta;
+        if (store_tile<C>(job, out_a, out_b, row_base + pm * C::kRows, tile_rows[pm], gt, C::kGroupThreads) &&
+            job.status != nullptr)
+          atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_full_bar[g]);
+      }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// same arithmetic for rows that are only 4-byte aligned (odd block lengths / strides): TMA bulk copies need
+// 16-byte alignment, so this variant loads cooperatively, one stage, block barriers.  Correct, not tuned.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(C::kUnits, 1) de_psd_kernel_unaligned(const Job job)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* const buf = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
+  int row_in_tile, w;
+  unit_to_row_window<C>(tid, row_in_tile, w);
+  for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned row0 = tile * C::kRows;
+    const unsigned left = job.total_rows - row0;
+    const unsigned nrows = left < C::kRows ? left : C::kRows;
+    for (unsigned r = tid / 32; r < nrows; r += C::kUnits / 32) {
+      const float* src = job.in + row_offset(job, row0 + r, C::kWindows, nullptr);
+      for (int i = lane; i < C::kLoad; i += 32) buf[r * C::kRowStride + i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (static_cast<unsigned>(row_in_tile) < nrows) {
+      float e[5], psd[5], de[5];
+      window_band_energy<C::kNi, C::kHann, C::kVec>(buf + row_in_tile * C::kRowStride + w * C::kHop, e);
+      if (band_features(e, psd, de) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
+      int ob;
+      row_offset(job, row0 + row_in_tile, C::kWindows, &ob);
+      const int o = ob + w * static_cast<int>(job.n_ch) * 5;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        job.de[o + b] = de[b];
+        job.psd[o + b] = psd[b];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -212,7 +452,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const unsigned char* _
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = i / per_row;
     const int v = static_cast<int>(i - row * per_row);
-    const unsigned char* s = src + row_offset(geom, row) * esize;
+    const unsigned char* s = src + row_offset(geom, static_cast<unsigned>(row), 1, nullptr) * esize;
     reinterpret_cast<vec_t*>(dst + row * row_bytes)[v] = reinterpret_cast<const vec_t*>(s)[v];
   }
 }
@@ -256,22 +496,62 @@ static int sm_count()
   return n;
 }
 
+// One launch over `job.total_rows` rows (< 2^31, output indices < 2^31: guaranteed by run_units()).
 template <class C>
-static int launch(const Job& job, cudaStream_t stream)
+static int launch(const Job& job, bool aligned16, cudaStream_t stream)
 {
   if (job.total_rows == 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+  const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
+  if (aligned16) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      configured = true;
+    }
+    unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
+    if (grid > n_tiles) grid = n_tiles;
+    de_psd_kernel<C><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+  } else {
+    static bool configured = false;
+    const int smem = C::kSlotFloats * 4;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(de_psd_kernel_unaligned<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      configured = true;
+    }
+    unsigned grid = static_cast<unsigned>(sm_count()) * 2;
+    if (grid > n_tiles) grid = n_tiles;
+    de_psd_kernel_unaligned<C><<<grid, C::kUnits, smem, stream>>>(job);
   }
-  const long long n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
-  long long grid = static_cast<long long>(sm_count()) * C::kCtasPerSm;
-  if (grid > n_tiles) grid = n_tiles;
-  de_psd_kernel<C><<<static_cast<unsigned>(grid), C::kThreads, C::kSmemBytes, stream>>>(job);
   ++g_launches;
   return static_cast<int>(cudaGetLastError());
+}
+
+// Split a job of `n_units` units (each n_ch rows, n_windows windows per row) into launches whose row and output
+// indices fit 32 bits.  Units are consumed in multiples of `unit_quantum` (d1, so that the affine unit -> offset
+// map restarts cleanly); `in_step` is the input offset (elements) per quantum.
+template <class C>
+static int run_units(Job job, long long n_units, long long unit_quantum, long long in_step, bool aligned16,
+                     cudaStream_t stream)
+{
+  const long long out_per_unit = static_cast<long long>(job.n_ch) * C::kWindows * 5;
+  long long max_units = ((1LL << 31) - 1) / out_per_unit;
+  max_units -= max_units % unit_quantum;
+  if (max_units < unit_quantum) return EEGFE_EINVAL;
+  const float* in0 = job.in;
+  float* de0 = job.de;
+  float* psd0 = job.psd;
+  for (long long done = 0; done < n_units; done += max_units) {
+    const long long n = (n_units - done < max_units) ? (n_units - done) : max_units;
+    job.in = in0 + (done / unit_quantum) * in_step;
+    job.de = de0 + done * out_per_unit;
+    job.psd = psd0 + done * out_per_unit;
+    job.total_rows = static_cast<unsigned>(n * job.n_ch);
+    const int rc = launch<C>(job, aligned16, stream);
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 static bool is_aligned16(const void* p, std::initializer_list<long long> elem_strides, int esize)
@@ -293,18 +573,18 @@ static int esize_of(int dtype)
   }
 }
 
-static Job raw_geometry(int64_t n_blocks, int n_ch, int64_t block_stride, int64_t ch_stride, int fs = 200)
+// units = clips; clip (block, concept c, repetition r) starts at block * block_stride + c * 13 fs + 3 fs + r * 2 fs
+static Job raw_geometry(int n_ch, int64_t block_stride, int64_t ch_stride, int fs = 200)
 {
   Job j{};
-  j.total_rows = n_blocks * 200 * n_ch;      // 40 concepts x 5 repetitions per block
   j.base = 3LL * fs;                         // 3 s hint before each concept (segment_raw_signals_200Hz.py:58-62)
   j.s0 = block_stride;
-  j.s1 = 13LL * fs;                          // concept stride: 3 s hint + 5 x 2 s
-  j.s2 = 2LL * fs;                           // repetition stride: 2 s
-  j.d1 = 200;
+  j.s1 = 13 * fs;                            // concept stride: 3 s hint + 5 x 2 s
+  j.s2 = 2 * fs;                             // repetition stride: 2 s
+  j.d1 = 200;                                // 40 concepts x 5 repetitions per block
   j.d2 = 5;
   j.ch_stride = ch_stride;
-  j.n_ch = n_ch;
+  j.n_ch = static_cast<unsigned>(n_ch);
   return j;
 }
 
@@ -337,12 +617,13 @@ int eegfe_windows_per_clip(int mode)
   }
 }
 
-static int dispatch_clip_mode(int mode, Job& job, cudaStream_t stream)
+static int dispatch_clip_mode(int mode, const Job& job, long long n_units, long long quantum, long long in_step,
+                              bool aligned16, cudaStream_t stream)
 {
   switch (mode) {
-    case EEGFE_MODE_500MS: return launch<CfgSliding500>(job, stream);
-    case EEGFE_MODE_1S: return launch<CfgOneSec>(job, stream);
-    case EEGFE_MODE_2S: return launch<CfgTwoSec>(job, stream);
+    case EEGFE_MODE_500MS: return run_units<CfgSliding500>(job, n_units, quantum, in_step, aligned16, stream);
+    case EEGFE_MODE_1S: return run_units<CfgOneSec>(job, n_units, quantum, in_step, aligned16, stream);
+    case EEGFE_MODE_2S: return run_units<CfgTwoSec>(job, n_units, quantum, in_step, aligned16, stream);
     default: return EEGFE_EINVAL;
   }
 }
@@ -355,13 +636,13 @@ int eegfe_de_psd_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t 
   if (raw == nullptr || de == nullptr || psd == nullptr) return EEGFE_EINVAL;
   if (block_len < 40 * 2600) return EEGFE_ERANGE;
   if (ch_stride < block_len || block_stride < 0) return EEGFE_EINVAL;
-  Job job = raw_geometry(n_blocks, n_ch, block_stride, ch_stride);
+  Job job = raw_geometry(n_ch, block_stride, ch_stride);
   job.in = raw;
   job.de = de;
   job.psd = psd;
   job.status = status;
-  job.aligned16 = is_aligned16(raw, {block_stride, ch_stride}, 4);
-  return dispatch_clip_mode(mode, job, static_cast<cudaStream_t>(stream));
+  return dispatch_clip_mode(mode, job, n_blocks * 200, 200, block_stride,
+                            is_aligned16(raw, {block_stride, ch_stride}, 4), static_cast<cudaStream_t>(stream));
 }
 
 int eegfe_de_psd_from_clips(const float* clips, int64_t n_clips, int n_ch, int mode, float* de, float* psd,
@@ -375,14 +656,13 @@ int eegfe_de_psd_from_clips(const float* clips, int64_t n_clips, int n_ch, int m
   job.de = de;
   job.psd = psd;
   job.status = status;
-  job.total_rows = n_clips * n_ch;
   job.s0 = static_cast<long long>(n_ch) * 400;
   job.d1 = 1;
   job.d2 = 1;
   job.ch_stride = 400;
-  job.n_ch = n_ch;
-  job.aligned16 = is_aligned16(clips, {}, 4);
-  return dispatch_clip_mode(mode, job, static_cast<cudaStream_t>(stream));
+  job.n_ch = static_cast<unsigned>(n_ch);
+  return dispatch_clip_mode(mode, job, n_clips, 1, job.s0, is_aligned16(clips, {}, 4),
+                            static_cast<cudaStream_t>(stream));
 }
 
 int eegfe_de_psd_windows(const float* x, int64_t n_rows, int win_len, int64_t row_stride, float* de, float* psd,
@@ -396,17 +676,16 @@ int eegfe_de_psd_windows(const float* x, int64_t n_rows, int win_len, int64_t ro
   job.de = de;
   job.psd = psd;
   job.status = status;
-  job.total_rows = n_rows;
   job.s0 = row_stride;
   job.d1 = 1;
   job.d2 = 1;
   job.ch_stride = 0;
   job.n_ch = 1;
-  job.aligned16 = is_aligned16(x, {row_stride}, 4);
+  const bool a16 = is_aligned16(x, {row_stride}, 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (win_len == 100) return launch<CfgWin100>(job, s);
-  if (win_len == 200) return launch<CfgWin200>(job, s);
-  return launch<CfgTwoSec>(job, s);          // 400: only samples 0..199 influence the result (DE_PSD.py:58)
+  if (win_len == 100) return run_units<CfgWin100>(job, n_rows, 1, row_stride, a16, s);
+  if (win_len == 200) return run_units<CfgWin200>(job, n_rows, 1, row_stride, a16, s);
+  return run_units<CfgTwoSec>(job, n_rows, 1, row_stride, a16, s);   // 400: only samples 0..199 count (DE_PSD.py:58)
 }
 
 int eegfe_segment_clips(const void* raw, int dtype, int64_t n_blocks, int n_ch, int64_t block_len,
@@ -419,22 +698,31 @@ int eegfe_segment_clips(const void* raw, int dtype, int64_t n_blocks, int n_ch, 
   if (raw == nullptr || clips == nullptr) return EEGFE_EINVAL;
   if (block_len < 40LL * 13 * fs) return EEGFE_ERANGE;
   if (ch_stride < block_len || block_stride < 0) return EEGFE_EINVAL;
-  Job geom = raw_geometry(n_blocks, n_ch, block_stride, ch_stride, fs);
-  const long long n_rows = geom.total_rows;
+  Job geom = raw_geometry(n_ch, block_stride, ch_stride, fs);
   const int row_bytes = 2 * fs * es;
   const bool a16 = is_aligned16(raw, {block_stride, ch_stride, 3LL * fs, 13LL * fs, 2LL * fs}, es) &&
                    reinterpret_cast<uintptr_t>(clips) % 16 == 0;
   const int threads = 256;
   const int grid = sm_count() * 8;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const unsigned char* src = static_cast<const unsigned char*>(raw);
-  unsigned char* dst = static_cast<unsigned char*>(clips);
-  if (a16) gather_rows_kernel<16><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
-  else if (es == 8) gather_rows_kernel<8><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
-  else if (es == 4) gather_rows_kernel<4><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
-  else gather_rows_kernel<2><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
-  ++g_launches;
-  return static_cast<int>(cudaGetLastError());
+  // rows are indexed with 32 bits inside the kernel: go block-group by block-group
+  const long long rows_per_block = 200LL * n_ch;
+  long long max_blocks = ((1LL << 31) - 1) / rows_per_block;
+  if (max_blocks < 1) return EEGFE_EINVAL;
+  for (long long b0 = 0; b0 < n_blocks; b0 += max_blocks) {
+    const long long nb = (n_blocks - b0 < max_blocks) ? (n_blocks - b0) : max_blocks;
+    const long long n_rows = nb * rows_per_block;
+    const unsigned char* src = static_cast<const unsigned char*>(raw) + b0 * block_stride * es;
+    unsigned char* dst = static_cast<unsigned char*>(clips) + b0 * rows_per_block * row_bytes;
+    if (a16) gather_rows_kernel<16><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
+    else if (es == 8) gather_rows_kernel<8><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
+    else if (es == 4) gather_rows_kernel<4><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
+    else gather_rows_kernel<2><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
+    ++g_launches;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return 0;
 }
 
 int eegfe_sliding_windows(const void* clips, int dtype, int64_t n_clips, int n_ch, void* windows, void* stream)

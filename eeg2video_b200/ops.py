@@ -39,7 +39,7 @@ def _stream(t):
 def de_psd_from_raw(raw: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """raw float32 (n_blocks, n_ch, T), last axis contiguous -> de, psd float32 (n_blocks*200, W, n_ch, 5)."""
     _require_cuda(raw, "raw")
-    if raw.dim() != 3 or raw.dtype != torch.float32 or (raw.shape[2] > 1 and raw.stride(2) != 1):
+    if raw.dim() != 3 or raw.dtype != torch.float32 or (raw.numel() > 0 and raw.stride(2) != 1):
         raise ValueError("raw must be float32 (n_blocks, n_ch, T) with a contiguous time axis")
     if mode not in WINDOWS_PER_CLIP:
         raise ValueError(f"unknown mode {mode}")
@@ -91,7 +91,8 @@ def _(clips, mode):
 def de_psd_windows(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """x float32 (n_rows, L), L in {100, 200, 400}, unit stride along L -> de, psd float32 (n_rows, 5)."""
     _require_cuda(x, "x")
-    if x.dim() != 2 or x.dtype != torch.float32 or x.shape[1] not in (100, 200, 400) or x.stride(1) != 1:
+    if x.dim() != 2 or x.dtype != torch.float32 or x.shape[1] not in (100, 200, 400) or \
+            (x.numel() > 0 and x.stride(1) != 1):
         raise ValueError("x must be float32 (n_rows, L) with L in {100, 200, 400} and unit stride along L")
     n_rows, length = x.shape
     row_stride = x.stride(0) if n_rows > 1 else length
@@ -114,7 +115,7 @@ def _(x):
 def segment_clips(raw: torch.Tensor, fs: int) -> torch.Tensor:
     """raw (n_blocks, n_ch, T) of a 2/4/8-byte dtype -> clips (n_blocks*200, n_ch, 2*fs), bit-exact gather."""
     _require_cuda(raw, "raw")
-    if raw.dim() != 3 or raw.dtype not in _COPY_DTYPES or (raw.shape[2] > 1 and raw.stride(2) != 1):
+    if raw.dim() != 3 or raw.dtype not in _COPY_DTYPES or (raw.numel() > 0 and raw.stride(2) != 1):
         raise ValueError("raw must be (n_blocks, n_ch, T) float32/float64/float16/int16 with a contiguous time axis")
     n_blocks, n_ch, t_len = raw.shape
     with torch.cuda.device(raw.device):

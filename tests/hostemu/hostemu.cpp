@@ -6,6 +6,7 @@
 // to what the device code computes (same operations, same order, IEEE fp32 add / mul / fma).
 #include <cstdint>
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 #include "../../eeg2video_b200/csrc/bandpower.cuh"
 
 extern "C" {
@@ -14,19 +15,19 @@ extern "C" {
 // energy: n_windows x 5 float32, E_b = sum_{k in band b} |X[k]|^2.
 int hostemu_band_energy(const float* x, int64_t n_windows, int len, float* energy)
 {
-  alignas(8) float buf[200];
+  alignas(16) float buf[200];
   for (int64_t w = 0; w < n_windows; ++w) {
     const float* row = x + w * len;
     float e[5];
     if (len == 100) {
       for (int i = 0; i < 100; ++i) buf[i] = row[i];
-      eegfe::window_band_energy<4, eegfe::kHannHalfSec>(buf, e);
+      eegfe::window_band_energy<4, eegfe::kHannHalfSec, 2>(buf, e);
     } else if (len == 200) {
       for (int i = 0; i < 200; ++i) buf[i] = row[i];
-      eegfe::window_band_energy<8, eegfe::kHannOneSec>(buf, e);
+      eegfe::window_band_energy<8, eegfe::kHannOneSec, 4>(buf, e);
     } else if (len == 400) {
       for (int i = 0; i < 200; ++i) buf[i] = row[i];
-      eegfe::window_band_energy<8, eegfe::kHannTwoSec>(buf, e);
+      eegfe::window_band_energy<8, eegfe::kHannTwoSec, 4>(buf, e);
     } else {
       return 1;
     }
