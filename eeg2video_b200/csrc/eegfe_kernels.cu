@@ -37,7 +37,7 @@ struct Job {
 
 // per-mode compile-time geometry
 template <int LOAD_, int NWIN_, int HOP_, int NI_, int HANN_, int ROWS_, int GROUPS_, int SLOTS_, int CTAS_, int PAD_,
-          int VEC_, int SPLIT_, bool LANEMAP_, bool GSTORE_>
+          int VEC_, int SPLIT_, bool LANEMAP_, bool GSTORE_, int PRODUCERS_>
 struct Cfg {
   static constexpr int kLoad = LOAD_;        // samples fetched per row
   static constexpr int kWindows = NWIN_;     // analysis windows per row
@@ -57,7 +57,8 @@ struct Cfg {
   static constexpr int kGroupThreads = kUnits * SPLIT_;        // worker threads per group
   static constexpr int kGroupWarps = kGroupThreads / 32;
   static constexpr int kWorkers = kGroupThreads * GROUPS_;
-  static constexpr int kThreads = kWorkers + 32;               // + one producer / storer warp
+  static constexpr int kProducers = PRODUCERS_;                // producer warps; warp p loads tiles p, p + P, ...
+  static constexpr int kThreads = kWorkers + 32 * PRODUCERS_;
   static constexpr int kRowBytes = LOAD_ * 4;
   static constexpr int kSlotFloats = ROWS_ * kRowStride;
   static constexpr int kOutFloats = kUnits * 5;                // per staging array, laid out [row][window][band]
@@ -68,6 +69,7 @@ struct Cfg {
   static_assert(SPLIT_ == 1 || SPLIT_ == 2, "one or two threads per channel-window");
   static_assert(SPLIT_ == 1 || GSTORE_, "split sweeps are combined by the group");
   static_assert(GROUPS_ <= 15, "one named barrier per group");
+  static_assert(PRODUCERS_ == 1 || GSTORE_, "the storer role is tied to a single producer warp");
   static_assert(SLOTS_ >= 2 * GROUPS_, "geometry ring safety: tile m is written out before tile m + 2 kSlots is loaded");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
@@ -81,13 +83,15 @@ struct Cfg {
 // leaves the producer warp time to double as the storer.  The 1 s / 2 s / pre-cut kernels are HBM-bound at 800 B
 // (400 B) per channel-window and want ~100 KB per SM in flight, hence small tiles, four groups and as many surplus
 // slots as shared memory holds; a tile is due every ~1 us per SM there, too fast for one warp to also write the
-// features, so each group stores its own tile (kGroupStore) and the producer only issues copies.
-//                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP GSTORE
-using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, false>;   // 224 + 32 thr, 110 KB x 2
-using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 4, 8, 1, 4, 4, 2, false, true>;   // 4 x 64 + 32 thr, 212 KB
-using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, true>;     // 4 x 64 + 32 (samples 0..199)
-using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, true>;    // 4 x 64 + 32, pre-cut 500 ms
-using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 4, 8, 1, 4, 4, 2, false, true>;     // 4 x 64 + 32, pre-cut 1 s
+// features, so each group stores its own tile (kGroupStore) and the producers only issue copies.  One bulk copy
+// per row costs a producer warp ~30 issue cycles (the TMA operands are per-lane, the instruction is uniform), so
+// 32 copies of 800 B per 26 KB tile keep one warp busy ~0.5 us: two producer warps where rows are short.
+//                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP GSTORE PROD
+using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, false, 1>;  // 224 + 32 thr, 110 KB x 2
+using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 4, 8, 1, 4, 4, 2, false, true, 2>;  // 4 x 64 + 64 thr, 212 KB
+using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, true, 2>;    // 4 x 64 + 64 (samples 0..199)
+using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, true, 2>;   // 4 x 64 + 64, pre-cut 500 ms
+using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 4, 8, 1, 4, 4, 2, false, true, 2>;    // 4 x 64 + 64, pre-cut 1 s
 
 __constant__ unsigned char c_lane_map_500[224] = {EEGFE_LANE_MAP_500};
 
@@ -284,7 +288,8 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
     // ------------------------------------------------ producer / storer warp ------------------------------------
     // Two cursors: loads run ahead as far as the ring has free slots; with !kGroupStore finished tiles are also
     // written out here, in order, whenever their group has staged them.  Neither role ever blocks the other.
-    int next_load = 0, next_store = C::kGroupStore ? n_mine : 0;
+    const int producer = (tid - C::kWorkers) / 32;
+    int next_load = producer, next_store = C::kGroupStore ? n_mine : 0;
     while (next_load < n_mine || next_store < n_mine) {
       bool progressed = false;
       if (next_load < n_mine) {
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
             bulk_copy_g2s(ring + s * C::kSlotFloats + r * C::kRowStride, job.in + off, C::kRowBytes, &full_bar[s]);
           }
           __syncwarp();
-          ++next_load;
+          next_load += C::kProducers;
           progressed = true;
         }
       }
