@@ -29,6 +29,25 @@ if ROOT not in sys.path:
 CW_PER_SUBJECT = {"500ms": 7 * 40 * 5 * 7 * 62, "1s": 7 * 40 * 5 * 2 * 62, "2s": 7 * 40 * 5 * 62}
 # algorithmic bytes per channel-window (SURVEY.md 8d / BASELINE.md 4): live input samples + 40 B of features
 BYTES_PER_CW = {"500ms": 1600.0 / 7 + 40, "1s": 840.0, "2s": 840.0}
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Everything that libraries print to fd 1 (NCCL's version banner, warnings) goes to stderr; the JSON line is
+    the only thing written to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 METRIC = "de_psd_channel_windows_per_s"
 UNIT = "channel-windows/s"
 
@@ -132,7 +151,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -350,21 +369,27 @@ def run_gpu_arm(args):
     # ---- final gather of the feature tensors to rank 0 (the only collective; reported, not in `value`) ----
     gather = None
     if world > 1:
-        shape = (S,) + tuple(de_buf.shape)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        full_de = cohort.gather_to_rank0(de_buf.reshape((S, -1)), S * world)
-        full_psd = cohort.gather_to_rank0(psd_buf.reshape((S, -1)), S * world)
+        reps = 3
+        for i in range(1 + reps):                 # first pass warms up the NCCL channels, untimed
+            if i == 1:
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+            full_de = cohort.gather_to_rank0(de_buf.reshape((S, -1)), S * world)
+            full_psd = cohort.gather_to_rank0(psd_buf.reshape((S, -1)), S * world)
         g1.record()
         barrier()
-        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        gather_ok = True
+        if rank == 0:
+            gather_ok = bool(torch.equal(full_de[:S].reshape(de_buf.shape), de_buf))
+        gms = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
         dist.all_reduce(gms, op=dist.ReduceOp.MAX)
         nbytes = 2 * de_buf.numel() * 4 * (world - 1)
         gather = {"ms": float(gms.item()), "bytes_into_rank0": nbytes,
                   "gbs_into_rank0": nbytes / (float(gms.item()) * 1e-3) / 1e9,
-                  "value_with_gather": world * cw_step_gpu / ((elapsed_ms / args.steps + float(gms.item())) * 1e-3)}
-        del full_de, full_psd, shape
+                  "value_with_gather": world * cw_step_gpu / ((elapsed_ms / args.steps + float(gms.item())) * 1e-3),
+                  "rank0_slice_matches": gather_ok}
+        del full_de, full_psd
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -381,10 +406,10 @@ def run_gpu_arm(args):
         cpu = None
         if not args.skip_cpu_baseline and world == 1:
             arm = CpuArm(mode)
-            cw, s = arm.run(args.cpu_clips_per_step * 4)
+            cw, s = arm.run(args.cpu_clips_per_step * 24)
             arm.close()
             cpu = {"value": cw / s, "unit": UNIT, "cores": arm.cores, "kind": "port",
-                   "sample": f"{arm.cores} workers x {args.cpu_clips_per_step * 4} synthetic 2 s clips (62 ch) each, "
+                   "sample": f"{arm.cores} workers x {args.cpu_clips_per_step * 24} synthetic 2 s clips (62 ch) each, "
                              f"mode {mode}, oracle.de_psd_loop (loop-for-loop port of DE_PSD.py:8-71), {s:.1f} s"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -392,16 +417,17 @@ def run_gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, _lib.launch_geometry(mode_id)),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(raw_host.numel() * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes(S * 7)),
                     "d2h_bytes_per_step": int(2 * de_host.numel() * 4), "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_result": e2e_ok,
-                    "path": "pinned host -> HostPipeline (chunked H2D / fused kernel / D2H on 3 streams) -> pinned host"},
+                    "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
+                            "D2H of DE+PSD, 3 streams) -> pinned host features"},
             "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         }
         if gather:
             line["gather"] = gather
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -422,6 +448,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

@@ -650,6 +650,38 @@ int eegfe_de_psd_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t 
                             is_aligned16(raw, {block_stride, ch_stride}, 4), static_cast<cudaStream_t>(stream));
 }
 
+int eegfe_de_psd_from_concepts(const float* x, int64_t n_blocks, int n_ch, int64_t block_stride, int64_t ch_stride,
+                               int64_t concept_stride, int64_t first_offset, int mode, float* de, float* psd,
+                               int* status, void* stream)
+{
+  if (n_blocks < 0 || n_ch <= 0 || eegfe_windows_per_clip(mode) < 0) return EEGFE_EINVAL;
+  if (n_blocks == 0) return 0;
+  if (x == nullptr || de == nullptr || psd == nullptr) return EEGFE_EINVAL;
+  if (concept_stride < 2000 || first_offset < 0 || concept_stride > 0x7fffffff) return EEGFE_EINVAL;
+  if (ch_stride < first_offset + 39 * concept_stride + 2000 || block_stride < 0) return EEGFE_ERANGE;
+  Job job = raw_geometry(n_ch, block_stride, ch_stride);
+  job.base = first_offset;
+  job.s1 = static_cast<int>(concept_stride);
+  job.in = x;
+  job.de = de;
+  job.psd = psd;
+  job.status = status;
+  return dispatch_clip_mode(mode, job, n_blocks * 200, 200, block_stride,
+                            is_aligned16(x, {block_stride, ch_stride, concept_stride, first_offset}, 4),
+                            static_cast<cudaStream_t>(stream));
+}
+
+int eegfe_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
+                       int64_t height, int kind, void* stream)
+{
+  if (dst == nullptr || src == nullptr || width < 0 || height < 0 || (kind != 1 && kind != 2)) return EEGFE_EINVAL;
+  if (width == 0 || height == 0) return 0;
+  return static_cast<int>(cudaMemcpy2DAsync(dst, static_cast<size_t>(dst_pitch), src, static_cast<size_t>(src_pitch),
+                                            static_cast<size_t>(width), static_cast<size_t>(height),
+                                            kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                            static_cast<cudaStream_t>(stream)));
+}
+
 int eegfe_de_psd_from_clips(const float* clips, int64_t n_clips, int n_ch, int mode, float* de, float* psd,
                             int* status, void* stream)
 {

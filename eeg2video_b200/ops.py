@@ -62,6 +62,33 @@ def _(raw, mode):
     return de, torch.empty_like(de), raw.new_empty((1,), dtype=torch.int32)
 
 
+@torch.library.custom_op("eeg2video::de_psd_from_concepts", mutates_args=(), device_types="cuda")
+def de_psd_from_concepts(x: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x float32 contiguous (n_blocks, n_ch, 40, 2000): the 5 x 400 live samples of every concept, hint periods
+    dropped -> de, psd float32 (n_blocks*200, W, n_ch, 5).  Same numbers as de_psd_from_raw on the full recording."""
+    _require_cuda(x, "x")
+    if x.dim() != 4 or x.shape[2] != 40 or x.shape[3] != 2000 or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("x must be contiguous float32 (n_blocks, n_ch, 40, 2000)")
+    if mode not in WINDOWS_PER_CLIP:
+        raise ValueError(f"unknown mode {mode}")
+    n_blocks, n_ch = x.shape[0], x.shape[1]
+    n_win = WINDOWS_PER_CLIP[mode]
+    with torch.cuda.device(x.device):
+        de = torch.empty((n_blocks * 200, n_win, n_ch, 5), dtype=torch.float32, device=x.device)
+        psd = torch.empty_like(de)
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.check(_lib.load().eegfe_de_psd_from_concepts(
+            x.data_ptr(), n_blocks, n_ch, n_ch * 80000, 80000, 2000, 0, mode,
+            de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(x)))
+    return de, psd, status
+
+
+@de_psd_from_concepts.register_fake
+def _(x, mode):
+    de = x.new_empty((x.shape[0] * 200, WINDOWS_PER_CLIP[mode], x.shape[1], 5), dtype=torch.float32)
+    return de, torch.empty_like(de), x.new_empty((1,), dtype=torch.int32)
+
+
 @torch.library.custom_op("eeg2video::de_psd_from_clips", mutates_args=(), device_types="cuda")
 def de_psd_from_clips(clips: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """clips float32 contiguous (n_clips, n_ch, 400) -> de, psd float32 (n_clips, W, n_ch, 5)."""

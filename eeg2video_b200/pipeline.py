@@ -2,27 +2,38 @@
 
 Recordings are streamed through the GPU in chunks of whole blocks: the H2D copy of chunk i+1 (copy stream),
 the fused kernel on chunk i (compute stream) and the D2H copy of chunk i-1's features (second copy stream)
-overlap, so the end-to-end rate is the PCIe rate of the raw samples, not the sum of the three.
+overlap, so the end-to-end rate is the PCIe rate of the samples that have to cross, not the sum of the three.
+
+Only the live samples cross PCIe: a SEED-DV block is 40 concepts x (600 hint + 2000 clip) samples, so each
+channel row is uploaded with ONE strided DMA (cudaMemcpy2DAsync: 40 pieces of 8000 B out of every 10400 B) into a
+compact (blocks, channels, 40, 2000) staging tensor -- 23 % fewer bytes than the raw row -- and the kernel reads
+that layout directly (eegfe_de_psd_from_concepts).
 """
 import torch
 
 from . import _lib, frontend, ops
+
+CONCEPTS, HINT, CLIPS_LEN, CONCEPT_LEN = 40, 600, 2000, 2600
 
 
 class HostPipeline:
     """Reusable staging buffers + streams for `features_from_host`.
 
     n_ch, block_len: recording geometry; chunk_blocks: blocks per in-flight chunk (two chunks are staged).
+    compact: upload only the 2000 live samples of every 2600 (needs block_len >= 104000).
     """
 
-    def __init__(self, device, n_ch=62, block_len=104000, chunk_blocks=28, mode="500ms"):
+    def __init__(self, device, n_ch=62, block_len=104000, chunk_blocks=28, mode="500ms", compact=True):
         self.device = torch.device(device)
         self.mode = frontend._mode_id(mode)
         self.n_win = ops.WINDOWS_PER_CLIP[self.mode]
         self.n_ch, self.block_len, self.chunk_blocks = n_ch, block_len, chunk_blocks
+        self.compact = bool(compact)
+        if block_len < CONCEPTS * CONCEPT_LEN:
+            raise RuntimeError("Segment length mismatch")
         with torch.cuda.device(self.device):
-            self.stage = [torch.empty((chunk_blocks, n_ch, block_len), dtype=torch.float32, device=self.device)
-                          for _ in range(2)]
+            shape = (chunk_blocks, n_ch, CONCEPTS, CLIPS_LEN) if self.compact else (chunk_blocks, n_ch, block_len)
+            self.stage = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
             self.h2d = torch.cuda.Stream()
             self.d2h = torch.cuda.Stream()
             self.compute = torch.cuda.Stream()
@@ -30,9 +41,34 @@ class HostPipeline:
     def feature_shape(self, n_blocks):
         return (n_blocks * 200, self.n_win, self.n_ch, 5)
 
+    def h2d_bytes(self, n_blocks):
+        per_row = CONCEPTS * CLIPS_LEN if self.compact else self.block_len
+        return n_blocks * self.n_ch * per_row * 4
+
+    def _upload(self, buf, raw_host, lo, hi):
+        if not self.compact:
+            buf.copy_(raw_host[lo:hi], non_blocking=True)
+            return
+        lib = _lib.load()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.block_len == CONCEPTS * CONCEPT_LEN:
+            # rows are back to back: the whole chunk is one uniform 2-D pattern
+            src = raw_host.data_ptr() + (lo * self.n_ch * self.block_len + HINT) * 4
+            _lib.check(lib.eegfe_copy2d_async(buf.data_ptr(), CLIPS_LEN * 4, src, CONCEPT_LEN * 4, CLIPS_LEN * 4,
+                                              (hi - lo) * self.n_ch * CONCEPTS, 1, stream))
+        else:
+            for b in range(lo, hi):
+                for ch in range(self.n_ch):
+                    src = raw_host.data_ptr() + ((b * self.n_ch + ch) * self.block_len + HINT) * 4
+                    dst = buf.data_ptr() + ((b - lo) * self.n_ch + ch) * CONCEPTS * CLIPS_LEN * 4
+                    _lib.check(lib.eegfe_copy2d_async(dst, CLIPS_LEN * 4, src, CONCEPT_LEN * 4, CLIPS_LEN * 4,
+                                                      CONCEPTS, 1, stream))
+
     def run(self, raw_host, de_host, psd_host):
-        """raw_host: pinned float32 (n_blocks, n_ch, block_len); de_host / psd_host: pinned float32
+        """raw_host: pinned, contiguous float32 (n_blocks, n_ch, block_len); de_host / psd_host: pinned float32
         feature_shape(n_blocks).  Returns the accumulated status flags (int).  Synchronises before returning."""
+        if not (raw_host.is_contiguous() and raw_host.dtype == torch.float32):
+            raise ValueError("raw_host must be contiguous float32")
         n_blocks = raw_host.shape[0]
         cb = self.chunk_blocks
         status_all = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -44,12 +80,15 @@ class HostPipeline:
                 with torch.cuda.stream(self.h2d):
                     if staged[i & 1] is not None:
                         self.h2d.wait_event(staged[i & 1])
-                    buf.copy_(raw_host[lo:hi], non_blocking=True)
+                    self._upload(buf, raw_host, lo, hi)
                     ready = torch.cuda.Event()
                     ready.record(self.h2d)
                 with torch.cuda.stream(self.compute):
                     self.compute.wait_event(ready)
-                    de, psd, status = ops.de_psd_from_raw(buf, self.mode)
+                    if self.compact:
+                        de, psd, status = ops.de_psd_from_concepts(buf, self.mode)
+                    else:
+                        de, psd, status = ops.de_psd_from_raw(buf, self.mode)
                     status_all |= status
                     done = torch.cuda.Event()
                     done.record(self.compute)
@@ -65,14 +104,16 @@ class HostPipeline:
             return int(status_all.item())
 
 
-def features_from_host(raw_host, mode="500ms", chunk_blocks=28, device="cuda", check=True):
+def features_from_host(raw_host, mode="500ms", chunk_blocks=28, device="cuda", check=True, compact=True):
     """Convenience wrapper: (.., 62, T) host tensor/array -> (de, psd) host tensors in the reference layout."""
     raw = torch.as_tensor(raw_host)
     lead = raw.shape[:-2]
     flat = raw.reshape((-1,) + tuple(raw.shape[-2:]))
+    if flat.dtype != torch.float32:
+        flat = flat.to(torch.float32)
     if not flat.is_pinned():
         flat = flat.contiguous().pin_memory()
-    pipe = HostPipeline(device, flat.shape[1], flat.shape[2], min(chunk_blocks, max(flat.shape[0], 1)), mode)
+    pipe = HostPipeline(device, flat.shape[1], flat.shape[2], min(chunk_blocks, max(flat.shape[0], 1)), mode, compact)
     shape = pipe.feature_shape(flat.shape[0])
     de = torch.empty(shape, dtype=torch.float32).pin_memory()
     psd = torch.empty(shape, dtype=torch.float32).pin_memory()

@@ -76,6 +76,25 @@ int eegfe_de_psd_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t 
                           float* de, float* psd, int* status, void* stream);
 
 /*
+ * Same as eegfe_de_psd_from_raw for recordings whose 3 s hint periods have been dropped or moved: concept c of a
+ * block starts at sample `first_offset + c * concept_stride` and holds its 5 repetitions back to back (5 x 400
+ * samples).  eegfe_de_psd_from_raw is the special case first_offset = 600, concept_stride = 2600.  Used by the
+ * host pipeline, which uploads only the 2000 live samples of every 2600 (one strided DMA per chunk, 23 % fewer
+ * PCIe bytes): first_offset = 0, concept_stride = 2000, ch_stride = 80000.
+ */
+int eegfe_de_psd_from_concepts(const float* x, int64_t n_blocks, int n_ch, int64_t block_stride, int64_t ch_stride,
+                               int64_t concept_stride, int64_t first_offset, int mode,
+                               float* de, float* psd, int* status, void* stream);
+
+/*
+ * Strided host <-> device row copy on `stream` (cudaMemcpy2DAsync): `height` rows of `width` bytes, source /
+ * destination pitches in bytes.  kind: 1 = host to device, 2 = device to host.  Plumbing for the host pipeline
+ * (PyTorch has no strided pinned-memory DMA); no arithmetic.
+ */
+int eegfe_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
+                       int64_t height, int kind, void* stream);
+
+/*
  * DE/PSD of already segmented 2 s clips.
  * Replaces: extract_de_psd_raw (1per2s.py:16-28), the 1 s script body (1per1s.py:24-58) and -- fused with
  *           seg_sliding_window -- extract_de_psd_sw (1per500ms.py:12-29).

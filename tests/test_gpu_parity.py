@@ -281,3 +281,33 @@ def test_unaligned_block_length_uses_fallback_loader():
     aligned = raw[..., :104000].contiguous()
     de_a, psd_a = frontend.de_psd_from_raw(aligned, "500ms")
     assert torch.equal(de, de_a) and torch.equal(psd, psd_a)
+
+
+# ---- host pipeline / compact layout -----------------------------------------------------------------------------------
+def test_from_concepts_equals_from_raw(subject):
+    raw, _ = subject
+    blocks = raw[:3]
+    compact = blocks.reshape(3, 62, 40, 2600)[..., 600:].contiguous()          # (3, 62, 40, 2000)
+    for mode in ("500ms", "1s", "2s"):
+        a = ops.de_psd_from_raw(blocks, frontend.MODES[mode])
+        b = ops.de_psd_from_concepts(compact, frontend.MODES[mode])
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("compact", (True, False))
+@pytest.mark.parametrize("block_len", (104000, 104400))
+def test_host_pipeline_matches_device_path(compact, block_len):
+    from eeg2video_b200 import pipeline
+    raw = synth.synth_blocks(5, 31, device=DEV, block_len=block_len)
+    want_de, want_psd = frontend.de_psd_from_raw(raw, "500ms")
+    de, psd = pipeline.features_from_host(raw.cpu(), "500ms", chunk_blocks=2, device=DEV, compact=compact)
+    assert not de.is_cuda and tuple(de.shape) == (5, 40, 5, 7, 62, 5)
+    assert torch.equal(de, want_de.cpu()) and torch.equal(psd, want_psd.cpu())
+
+
+def test_host_pipeline_zero_power_flag():
+    from eeg2video_b200 import pipeline
+    raw = synth.synth_blocks(1, 3, device="cpu")
+    raw[0, 5, 600:1000] = 0.0
+    with pytest.raises(ValueError, match="math domain error"):
+        pipeline.features_from_host(raw, "2s", device=DEV)
