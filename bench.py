@@ -321,10 +321,12 @@ def run_gpu_arm(args):
     launches_before = _lib.launch_count()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("eegfe_timed")        # ncu --nvtx --nvtx-include "eegfe_timed/" lists exactly this region
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
+    torch.cuda.nvtx.range_pop()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     gpu_launches = _lib.launch_count() - launches_before
@@ -353,11 +355,13 @@ def run_gpu_arm(args):
     pipe.run(raw_host, de_host, psd_host)                                   # warm-up
     barrier()
     launches_e2e0 = _lib.launch_count()
+    torch.cuda.nvtx.range_push("eegfe_e2e")
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         pipe.run(raw_host, de_host, psd_host)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    torch.cuda.nvtx.range_pop()
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

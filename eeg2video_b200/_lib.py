@@ -20,6 +20,9 @@ SIGNATURES = {
     "eegfe_windows_per_clip": (_int, [_int]),
     "eegfe_de_psd_from_raw": (_int, [_ptr, _i64, _int, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr]),
     "eegfe_de_psd_from_concepts": (_int, [_ptr, _i64, _int, _i64, _i64, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr]),
+    "eegfe_glmnet_inputs_from_raw": (_int, [_ptr, _i64, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                            _ptr]),
+    "eegfe_channel_stats": (_int, [_ptr, _i64, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "eegfe_copy2d_async": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "eegfe_de_psd_from_clips": (_int, [_ptr, _i64, _int, _int, _ptr, _ptr, _ptr, _ptr]),
     "eegfe_de_psd_windows": (_int, [_ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr]),

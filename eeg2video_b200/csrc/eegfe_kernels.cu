@@ -33,6 +33,11 @@ struct Job {
   long long ch_stride;    // elements between channel rows of one unit
   unsigned d1, d2;
   unsigned n_ch;
+  // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = x * scale[ch] + shift[ch]
+  float* norm_out;
+  const float* norm_scale;
+  const float* norm_shift;
+  long long norm_row0;    // global row index of this launch's first row (rows of earlier launches of a split job)
 };
 
 // per-mode compile-time geometry
@@ -249,7 +254,7 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
 // kSplit == 2: even-sweep warps and odd-sweep warps stage their partial band energies; the storer adds them
 //              and does the epilogue (the same additions, so the result is bit-identical to kSplit == 1).
 // ---------------------------------------------------------------------------------------------------------------
-template <class C>
+template <class C, bool NORM>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -370,6 +375,28 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           sweep_odd<C::kNi, C::kHann, C::kVec>(win, va);
         }
       }
+      if constexpr (NORM) {
+        // GLMNet raw branch: the staged clip rows leave again as per-channel normalised float32 clips.  Each warp
+        // of the group takes every kGroupWarps-th row; a row is 100 float4, stored coalesced.
+        static_assert(!NORM || (C::kLoad == 400 && C::kWindows == 7), "normalised clips ride on the 500 ms kernel");
+        const int nrows = tile_rows[m % C::kMeta];
+        const unsigned row0 = (blockIdx.x + static_cast<unsigned>(m) * gridDim.x) * C::kRows;
+        for (int r = gt / 32; r < nrows; r += C::kGroupWarps) {
+          const unsigned grow = row0 + r;
+          const unsigned ch = grow % job.n_ch;
+          const float sc = __ldg(job.norm_scale + ch), sh = __ldg(job.norm_shift + ch);
+          const float4* src = reinterpret_cast<const float4*>(ring + s * C::kSlotFloats + r * C::kRowStride);
+          float4* dst = reinterpret_cast<float4*>(job.norm_out + (job.norm_row0 + grow) * 400);
+          for (int i = lane; i < 100; i += 32) {
+            float4 v = src[i];
+            v.x = fmaf(v.x, sc, sh);
+            v.y = fmaf(v.y, sc, sh);
+            v.z = fmaf(v.z, sc, sh);
+            v.w = fmaf(v.w, sc, sh);
+            dst[i] = v;
+          }
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp no longer reads the input slot
       if constexpr (C::kGroupStore) {
@@ -486,6 +513,66 @@ __global__ void __launch_bounds__(256) sliding_windows_kernel(const unsigned cha
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// per-channel statistics of the clip samples (training-split normalisation of the GLMNet raw branch)
+// ---------------------------------------------------------------------------------------------------------------
+// One CTA per (block, channel) row: float64 sum and sum of squares over the 40 x 2000 clip samples of the row
+// (hint periods skipped), fixed reduction order -> deterministic.
+__global__ void __launch_bounds__(256) channel_row_sums_kernel(const float* __restrict__ raw, long long block_stride,
+                                                                long long ch_stride, int n_ch, double* __restrict__ partial)
+{
+  const long long row = blockIdx.x;
+  const long long blk = row / n_ch;
+  const int ch = static_cast<int>(row - blk * n_ch);
+  const float* base = raw + blk * block_stride + ch * ch_stride;
+  double s = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < 40 * 2000; i += 256) {
+    const int c = i / 2000;
+    const float v = __ldg(base + c * 2600 + 600 + (i - c * 2000));
+    s += v;
+    ss += static_cast<double>(v) * v;
+  }
+  __shared__ double sh_s[8], sh_ss[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    ss += __shfl_down_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh_s[threadIdx.x >> 5] = s;
+    sh_ss[threadIdx.x >> 5] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += sh_s[w];
+      b += sh_ss[w];
+    }
+    partial[2 * row] = a;
+    partial[2 * row + 1] = b;
+  }
+}
+
+// mean / population std per channel over the blocks selected by `mask` (one thread per channel, block order)
+__global__ void channel_stats_finish_kernel(const double* __restrict__ partial, const unsigned char* __restrict__ mask,
+                                            long long n_blocks, int n_ch, double* __restrict__ mean, double* __restrict__ std)
+{
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= n_ch) return;
+  double s = 0.0, ss = 0.0, n = 0.0;
+  for (long long b = 0; b < n_blocks; ++b) {
+    if (mask != nullptr && mask[b] == 0) continue;
+    s += partial[2 * (b * n_ch + ch)];
+    ss += partial[2 * (b * n_ch + ch) + 1];
+    n += 40.0 * 2000.0;
+  }
+  const double m = n > 0 ? s / n : 0.0;
+  const double var = n > 0 ? ss / n - m * m : 0.0;
+  mean[ch] = m;
+  std[ch] = sqrt(var > 0.0 ? var : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static long long g_launches = 0;
@@ -508,16 +595,31 @@ static int launch(const Job& job, bool aligned16, cudaStream_t stream)
   if (job.total_rows == 0) return 0;
   const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (aligned16) {
+    unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
+    if (grid > n_tiles) grid = n_tiles;
+    if constexpr (C::kLoad == 400 && C::kWindows == 7) {
+      if (job.norm_out != nullptr) {
+        static bool configured_norm = false;
+        if (!configured_norm) {
+          cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+          if (e != cudaSuccess) return static_cast<int>(e);
+          configured_norm = true;
+        }
+        de_psd_kernel<C, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+        ++g_launches;
+        return static_cast<int>(cudaGetLastError());
+      }
+    }
+    if (job.norm_out != nullptr) return EEGFE_EINVAL;
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+      cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
       if (e != cudaSuccess) return static_cast<int>(e);
       configured = true;
     }
-    unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
-    if (grid > n_tiles) grid = n_tiles;
-    de_psd_kernel<C><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+    de_psd_kernel<C, false><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
   } else {
+    if (job.norm_out != nullptr) return EEGFE_EINVAL;     // the normalised-clip product needs 16-byte aligned rows
     static bool configured = false;
     const int smem = C::kSlotFloats * 4;
     if (!configured) {
@@ -553,6 +655,7 @@ static int run_units(Job job, long long n_units, long long unit_quantum, long lo
     job.de = de0 + done * out_per_unit;
     job.psd = psd0 + done * out_per_unit;
     job.total_rows = static_cast<unsigned>(n * job.n_ch);
+    job.norm_row0 = done * job.n_ch;
     const int rc = launch<C>(job, aligned16, stream);
     if (rc != 0) return rc;
   }
@@ -669,6 +772,48 @@ int eegfe_de_psd_from_concepts(const float* x, int64_t n_blocks, int n_ch, int64
   return dispatch_clip_mode(mode, job, n_blocks * 200, 200, block_stride,
                             is_aligned16(x, {block_stride, ch_stride, concept_stride, first_offset}, 4),
                             static_cast<cudaStream_t>(stream));
+}
+
+int eegfe_glmnet_inputs_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len, int64_t block_stride,
+                                 int64_t ch_stride, const float* ch_scale, const float* ch_shift, float* clips_norm,
+                                 float* de, float* psd, int* status, void* stream)
+{
+  if (n_blocks < 0 || n_ch <= 0) return EEGFE_EINVAL;
+  if (n_blocks == 0) return 0;
+  if (raw == nullptr || de == nullptr || psd == nullptr || clips_norm == nullptr || ch_scale == nullptr ||
+      ch_shift == nullptr)
+    return EEGFE_EINVAL;
+  if (block_len < 40 * 2600) return EEGFE_ERANGE;
+  if (ch_stride < block_len || block_stride < 0) return EEGFE_EINVAL;
+  if (!is_aligned16(raw, {block_stride, ch_stride}, 4) || reinterpret_cast<uintptr_t>(clips_norm) % 16 != 0)
+    return EEGFE_EINVAL;
+  Job job = raw_geometry(n_ch, block_stride, ch_stride);
+  job.in = raw;
+  job.de = de;
+  job.psd = psd;
+  job.status = status;
+  job.norm_out = clips_norm;
+  job.norm_scale = ch_scale;
+  job.norm_shift = ch_shift;
+  return run_units<CfgSliding500>(job, n_blocks * 200, 200, block_stride, true, static_cast<cudaStream_t>(stream));
+}
+
+int eegfe_channel_stats(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len, int64_t block_stride,
+                        int64_t ch_stride, const unsigned char* block_mask, double* workspace, double* mean,
+                        double* std, void* stream)
+{
+  if (n_blocks < 0 || n_ch <= 0) return EEGFE_EINVAL;
+  if (raw == nullptr || workspace == nullptr || mean == nullptr || std == nullptr) return EEGFE_EINVAL;
+  if (block_len < 40 * 2600) return EEGFE_ERANGE;
+  if (ch_stride < block_len || block_stride < 0 || n_blocks * n_ch > 0x7fffffff) return EEGFE_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_blocks > 0) {
+    channel_row_sums_kernel<<<static_cast<unsigned>(n_blocks * n_ch), 256, 0, s>>>(raw, block_stride, ch_stride, n_ch, workspace);
+    ++g_launches;
+  }
+  channel_stats_finish_kernel<<<(n_ch + 63) / 64, 64, 0, s>>>(workspace, block_mask, n_blocks, n_ch, mean, std);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
 }
 
 int eegfe_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,

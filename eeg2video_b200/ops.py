@@ -175,3 +175,59 @@ def sliding_windows(clips: torch.Tensor) -> torch.Tensor:
 @sliding_windows.register_fake
 def _(clips):
     return clips.new_empty((clips.shape[0], 7, clips.shape[1], 100))
+
+
+@torch.library.custom_op("eeg2video::glmnet_inputs_from_raw", mutates_args=(), device_types="cuda")
+def glmnet_inputs_from_raw(raw: torch.Tensor, ch_scale: torch.Tensor, ch_shift: torch.Tensor
+                           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """raw float32 (n_blocks, n_ch, T) + per-channel scale / shift (float32, n_ch) ->
+    clips_norm (n_blocks*200, n_ch, 400), de, psd (n_blocks*200, 7, n_ch, 5), status."""
+    _require_cuda(raw, "raw")
+    if raw.dim() != 3 or raw.dtype != torch.float32 or (raw.numel() > 0 and raw.stride(2) != 1):
+        raise ValueError("raw must be float32 (n_blocks, n_ch, T) with a contiguous time axis")
+    n_blocks, n_ch, t_len = raw.shape
+    for name, v in (("ch_scale", ch_scale), ("ch_shift", ch_shift)):
+        if v.dtype != torch.float32 or v.shape != (n_ch,) or not v.is_contiguous() or v.device != raw.device:
+            raise ValueError(f"{name} must be a contiguous float32 ({n_ch},) tensor on {raw.device}")
+    with torch.cuda.device(raw.device):
+        clips = torch.empty((n_blocks * 200, n_ch, 400), dtype=torch.float32, device=raw.device)
+        de = torch.empty((n_blocks * 200, 7, n_ch, 5), dtype=torch.float32, device=raw.device)
+        psd = torch.empty_like(de)
+        status = torch.zeros(1, dtype=torch.int32, device=raw.device)
+        _lib.check(_lib.load().eegfe_glmnet_inputs_from_raw(
+            raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), ch_scale.data_ptr(),
+            ch_shift.data_ptr(), clips.data_ptr(), de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
+    return clips, de, psd, status
+
+
+@glmnet_inputs_from_raw.register_fake
+def _(raw, ch_scale, ch_shift):
+    clips = raw.new_empty((raw.shape[0] * 200, raw.shape[1], 400), dtype=torch.float32)
+    de = raw.new_empty((raw.shape[0] * 200, 7, raw.shape[1], 5), dtype=torch.float32)
+    return clips, de, torch.empty_like(de), raw.new_empty((1,), dtype=torch.int32)
+
+
+@torch.library.custom_op("eeg2video::channel_stats", mutates_args=(), device_types="cuda")
+def channel_stats(raw: torch.Tensor, block_mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """raw float32 (n_blocks, n_ch, T), block_mask uint8 (n_blocks,) -> per-channel (mean, std) float64 over the
+    clip samples of the selected blocks (population std)."""
+    _require_cuda(raw, "raw")
+    if raw.dim() != 3 or raw.dtype != torch.float32 or (raw.numel() > 0 and raw.stride(2) != 1):
+        raise ValueError("raw must be float32 (n_blocks, n_ch, T) with a contiguous time axis")
+    n_blocks, n_ch, t_len = raw.shape
+    if block_mask.dtype != torch.uint8 or block_mask.shape != (n_blocks,) or block_mask.device != raw.device:
+        raise ValueError("block_mask must be uint8 (n_blocks,) on the same device")
+    with torch.cuda.device(raw.device):
+        work = torch.empty((max(n_blocks * n_ch, 1), 2), dtype=torch.float64, device=raw.device)
+        mean = torch.empty(n_ch, dtype=torch.float64, device=raw.device)
+        std = torch.empty_like(mean)
+        _lib.check(_lib.load().eegfe_channel_stats(
+            raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1),
+            block_mask.contiguous().data_ptr(), work.data_ptr(), mean.data_ptr(), std.data_ptr(), _stream(raw)))
+    return mean, std
+
+
+@channel_stats.register_fake
+def _(raw, block_mask):
+    mean = raw.new_empty((raw.shape[1],), dtype=torch.float64)
+    return mean, torch.empty_like(mean)

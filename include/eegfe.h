@@ -87,6 +87,31 @@ int eegfe_de_psd_from_concepts(const float* x, int64_t n_blocks, int n_ch, int64
                                float* de, float* psd, int* status, void* stream);
 
 /*
+ * NEXT-ROW (BASELINE.json configs[4]): GLMNet input build in one pass over the raw recording.
+ * The reference describes it (README.md:80-81, :88, :97-99: "Raw EEGs are normalized per channel using the training
+ * split statistics"; model input contracts EEG-VP/models.py:119, :364) but its trainer / inference scripts are not in
+ * the tree, so this row has no reference code to pin against (oracle/glmnet_inputs.py states the arithmetic).
+ *
+ * clips_norm   float32 [n_blocks * 200][n_ch][400] = x * ch_scale[c] + ch_shift[c]   (scale = 1/std, shift = -mean/std);
+ *              viewed as (N, 1, n_ch, 400) it is the input of glfnet / shallownet.
+ * de, psd      float32 [n_blocks * 200][7][n_ch][5], the 500 ms features (identical to eegfe_de_psd_from_raw).
+ * Requires 16-byte aligned rows (block_len, strides multiples of 4 samples) -> EEGFE_EINVAL otherwise.
+ */
+int eegfe_glmnet_inputs_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len, int64_t block_stride,
+                                 int64_t ch_stride, const float* ch_scale, const float* ch_shift, float* clips_norm,
+                                 float* de, float* psd, int* status, void* stream);
+
+/*
+ * Per-channel mean and population standard deviation of the clip samples (hint periods excluded) over the blocks
+ * with block_mask[b] != 0 (NULL = all blocks): the "training split statistics" of the GLMNet raw branch.
+ * workspace    double [n_blocks * n_ch * 2] (device scratch);  mean, std: double [n_ch] (device).
+ * float64 accumulation in a fixed order (deterministic).
+ */
+int eegfe_channel_stats(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len, int64_t block_stride,
+                        int64_t ch_stride, const unsigned char* block_mask, double* workspace, double* mean,
+                        double* std, void* stream);
+
+/*
  * Strided host <-> device row copy on `stream` (cudaMemcpy2DAsync): `height` rows of `width` bytes, source /
  * destination pitches in bytes.  kind: 1 = host to device, 2 = device to host.  Plumbing for the host pipeline
  * (PyTorch has no strided pinned-memory DMA); no arithmetic.

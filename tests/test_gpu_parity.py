@@ -311,3 +311,37 @@ def test_host_pipeline_zero_power_flag():
     raw[0, 5, 600:1000] = 0.0
     with pytest.raises(ValueError, match="math domain error"):
         pipeline.features_from_host(raw, "2s", device=DEV)
+
+
+# ---- next row: GLMNet input build ---------------------------------------------------------------------------------------
+def test_glmnet_channel_stats_and_inputs(subject):
+    from eeg2video_b200 import glmnet_inputs
+    from oracle import glmnet_inputs as oracle_glm
+    raw, raw_np = subject
+    train = [0, 1, 2, 3, 4, 6]                                # leave block 5 out
+    mean, std = glmnet_inputs.channel_stats(raw, train)
+    mean_ref, std_ref = oracle_glm.channel_stats(raw_np, train)
+    assert np.allclose(mean.cpu().numpy(), mean_ref, rtol=0, atol=1e-9 * np.abs(mean_ref).max() + 1e-9)
+    assert np.allclose(std.cpu().numpy(), std_ref, rtol=1e-10)
+    mask = torch.zeros(7, dtype=torch.bool, device=DEV)
+    mask[train] = True
+    mean2, std2 = glmnet_inputs.channel_stats(raw, mask)
+    assert torch.equal(mean, mean2) and torch.equal(std, std2)
+
+    clips, de, psd = glmnet_inputs.build_inputs(raw, mean, std)
+    assert tuple(clips.shape) == (7, 40, 5, 1, 62, 400) and tuple(de.shape) == (7, 40, 5, 7, 62, 5)
+    want = oracle_glm.normalised_clips(raw_np, mean_ref, std_ref)
+    assert np.max(np.abs(clips.cpu().numpy() - want)) <= 2e-6           # fp32 fma(x, 1/std, -mean/std) vs float64
+    de0, psd0 = frontend.de_psd_from_raw(raw, "500ms")
+    assert torch.equal(de, de0) and torch.equal(psd, psd0)              # the feature product is unchanged
+    # the normalised clips have zero mean / unit std per channel over the training blocks
+    x = clips[train].double()
+    assert x.mean(dim=(0, 1, 2, 3, 5)).abs().max() < 1e-5
+    assert (x.std(dim=(0, 1, 2, 3, 5), unbiased=False) - 1).abs().max() < 1e-5
+
+
+def test_glmnet_inputs_need_aligned_rows():
+    from eeg2video_b200 import glmnet_inputs
+    raw = synth.synth_blocks(1, 3, device=DEV, channels=4, block_len=104001)
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        glmnet_inputs.build_inputs(raw, torch.zeros(4), torch.ones(4))
