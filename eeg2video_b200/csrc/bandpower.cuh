@@ -272,48 +272,47 @@ using Group = std::conditional_t<NI == 4, Group4<HANN, RHO, VEC>, Group8<HANN, R
 // NI = 4: `win` holds 100 samples (zero-padded transform);  NI = 8: `win` holds 200 samples.
 // The work is two independent sweeps over the window, each forming two radix-8 output sequences and running two
 // DFT-25 (100 registers of work set instead of 200):
-//   even sweep: harmonics k1 = 0, 4 (one shared DFT) and k1 = 2   -> part_even[b]
-//   odd  sweep: harmonics k1 = 1 and k1 = 3                        -> part_odd[b]
+//   sweep 0 (even): harmonics k1 = 0, 4 (one shared DFT) and k1 = 2   -> part_even[b]
+//   sweep 1 (odd) : harmonics k1 = 1 and k1 = 3                        -> part_odd[b]
 //   E_b = part_even[b] + part_odd[b]
 // A thread may run both (500 ms kernel) or the two sweeps may run in different warps (1 s / 2 s kernels); the
 // partial sums and their final addition are identical either way, so all paths agree bit for bit.
+//
+// CODE SIZE.  The sweep is selected at RUN time (a warp-uniform branch) so that both sweeps share the machine code
+// of the two DFT-25: fully unrolled, the four DFTs are 13.6 KB of SASS out of a 30 KB loop body, and B200's L1.5
+// instruction cache holds 32 KB -- above that every warp streams its instructions from L2 and the producer warp
+// starves on instruction fetch (ncu: stall_no_instruction 23 %).  Sharing the DFT code brings the whole kernel
+// to ~25 KB.  It also keeps the compiler from merging the two sweeps' loads and radix-8 partial sums (which cost
+// ~100 extra live registers).
 template <int NI, int HANN, int VEC>
-EEGFE_FN void sweep_even(const float* win, float (&part)[5])
+EEGFE_FN void sweep_any(const float* win, int sweep, float (&part)[5])
 {
   cf acc[5];
   static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_make(0.f, 0.f); });
-  cf b04[25], b2[25];
-  static_for<0, 25>([&](auto rho_) {
-    constexpr int rho = decltype(rho_)::value;
-    const Group<NI, HANN, rho, VEC> g(win);
-    g.even(b04[g.N2], b2[g.N2]);
-  });
-  dft25(b04);
-  accumulate_real_pair(b04, acc);
-  static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_mul_s(acc[decltype(b_)::value], 0.25f); });
-  dft25(b2);
-  accumulate_complex<2>(b2, acc);
-  static_for<0, 5>([&](auto b_) {
-    constexpr int b = decltype(b_)::value;
-    part[b] = f_add(c_re(acc[b]), c_im(acc[b]));
-  });
-}
-
-template <int NI, int HANN, int VEC>
-EEGFE_FN void sweep_odd(const float* win, float (&part)[5])
-{
-  cf acc[5];
-  static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_make(0.f, 0.f); });
-  cf b1[25], b3[25];
-  static_for<0, 25>([&](auto rho_) {
-    constexpr int rho = decltype(rho_)::value;
-    const Group<NI, HANN, rho, VEC> g(win);
-    g.odd(b1[g.N2], b3[g.N2]);
-  });
-  dft25(b1);
-  accumulate_complex<1>(b1, acc);
-  dft25(b3);
-  accumulate_complex<3>(b3, acc);
+  cf p[25], q[25];
+  if (sweep == 0) {
+    static_for<0, 25>([&](auto rho_) {
+      constexpr int rho = decltype(rho_)::value;
+      const Group<NI, HANN, rho, VEC> g(win);
+      g.even(p[g.N2], q[g.N2]);                       // p = B_0 + i B_4, q = B_2
+    });
+  } else {
+    static_for<0, 25>([&](auto rho_) {
+      constexpr int rho = decltype(rho_)::value;
+      const Group<NI, HANN, rho, VEC> g(win);
+      g.odd(p[g.N2], q[g.N2]);                        // p = B_1, q = B_3
+    });
+  }
+  dft25(p);
+  if (sweep == 0) {
+    accumulate_real_pair(p, acc);
+    static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_mul_s(acc[decltype(b_)::value], 0.25f); });
+  } else {
+    accumulate_complex<1>(p, acc);
+  }
+  dft25(q);
+  if (sweep == 0) accumulate_complex<2>(q, acc);
+  else accumulate_complex<3>(q, acc);
   static_for<0, 5>([&](auto b_) {
     constexpr int b = decltype(b_)::value;
     part[b] = f_add(c_re(acc[b]), c_im(acc[b]));
@@ -323,18 +322,19 @@ EEGFE_FN void sweep_odd(const float* win, float (&part)[5])
 template <int NI, int HANN, int VEC>
 EEGFE_FN void window_band_energy(const float* win, float (&energy)[5])
 {
-  float pe[5], po[5];
-  sweep_even<NI, HANN, VEC>(win, pe);
-  // Without this the compiler (nvcc AND ptxas) merges the sample loads and the radix-8 partial sums of the two
-  // sweeps and keeps ~100 extra values live across the first pair of DFTs -- exactly what the two sweeps are
-  // there to avoid.  The second sweep therefore reads through a pointer offset by a run-time zero.
-  asm volatile("" ::: "memory");
-  win += EEGFE_OPAQUE_ZERO();
-  sweep_odd<NI, HANN, VEC>(win, po);
-  static_for<0, 5>([&](auto b_) {
-    constexpr int b = decltype(b_)::value;
-    energy[b] = f_add(pe[b], po[b]);
-  });
+  float pe[5];
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int sweep = EEGFE_OPAQUE_ZERO(); sweep < 2; ++sweep) {
+    float part[5];
+    sweep_any<NI, HANN, VEC>(win, sweep, part);
+    static_for<0, 5>([&](auto b_) {
+      constexpr int b = decltype(b_)::value;
+      if (sweep == 0) pe[b] = part[b];
+      else energy[b] = f_add(pe[b], part[b]);
+    });
+  }
 }
 
 }  // namespace eegfe

@@ -66,16 +66,14 @@ struct Cfg {
   static constexpr int kThreads = kWorkers + 32 * PRODUCERS_;
   static constexpr int kRowBytes = LOAD_ * 4;
   static constexpr int kSlotFloats = ROWS_ * kRowStride;
-  static constexpr int kOutFloats = kUnits * 5;                // per staging array, laid out [row][window][band]
-  static constexpr int kMeta = 2 * SLOTS_;   // tile-geometry ring: a tile's entry must outlive its input slot (see kernel)
-  static constexpr int kSmemBytes = (SLOTS_ * kSlotFloats + GROUPS_ * 2 * kOutFloats) * 4 + kMeta * (ROWS_ + 1) * 4;
+  static constexpr int kOutFloats = kUnits * 5;                // per staging array, laid out [window][row][band]
+  static constexpr int kSmemBytes = (SLOTS_ * kSlotFloats + GROUPS_ * 2 * kOutFloats + kWorkers) * 4;
   static_assert(kUnits % 32 == 0, "a tile must fill whole warps");
   static_assert(kRowBytes % 16 == 0 && kRowStride % 4 == 0, "TMA bulk copies need 16-byte aligned rows");
   static_assert(SPLIT_ == 1 || SPLIT_ == 2, "one or two threads per channel-window");
   static_assert(SPLIT_ == 1 || GSTORE_, "split sweeps are combined by the group");
   static_assert(GROUPS_ <= 15, "one named barrier per group");
   static_assert(PRODUCERS_ == 1 || GSTORE_, "the storer role is tied to a single producer warp");
-  static_assert(SLOTS_ >= 2 * GROUPS_, "geometry ring safety: tile m is written out before tile m + 2 kSlots is loaded");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
 // Shared-memory bank rules behind PAD / VEC (B200: 32 banks x 4 B; 64-bit loads are served per half-warp,
@@ -183,34 +181,46 @@ __device__ __forceinline__ bool band_features(const float (&e)[5], float (&psd)[
   return zero;
 }
 
-// Write one staged tile to HBM.  Thread `t` of `nthreads` takes consecutive (row, band) of one window, i.e.
-// consecutive addresses while the rows stay inside a clip.  kSplit == 2: the two sweeps' partials are added and
-// turned into (psd, de) here.  Returns true if a zero-power band was seen (kSplit == 2 only).
+// Write one staged tile to HBM.  The staging arrays are laid out [window][row][band], the features in HBM
+// [clip][window][channel][band]: for one window, the rows of the tile that belong to the same clip form ONE
+// contiguous run of 5 * rows floats on both sides, so the copy is linear (no per-element index arithmetic) with
+// thread `t` of `nthreads` taking consecutive addresses.  A tile spans 1 + (kRows - 1) / n_ch clips at most.
+// kSplit == 2: the two sweeps' partials are added and turned into (psd, de) here.
+// Returns true if a zero-power band was seen (kSplit == 2 only).
 template <class C>
-__device__ __forceinline__ bool store_tile(const Job& job, const float* out_a, const float* out_b, const int* rbase,
+__device__ __forceinline__ bool store_tile(const Job& job, const float* out_a, const float* out_b, unsigned row0,
                                            int nrows, int t, int nthreads)
 {
   const int win_stride = static_cast<int>(job.n_ch) * 5;
   bool zero = false;
-#pragma unroll 4
-  for (int j = t; j < C::kOutFloats; j += nthreads) {
-    const int w = j / (C::kRows * 5);
-    const int rem = j - w * (C::kRows * 5);
-    const int r = rem / 5;
-    const int b = rem - r * 5;
-    if (r < nrows) {
-      const int e = (r * C::kWindows + w) * 5 + b;
-      const int o = rbase[r] + w * win_stride + b;
-      if constexpr (C::kSplit == 1) {
-        job.de[o] = out_a[e];
-        job.psd[o] = out_b[e];
-      } else {
-        const float p = __fadd_rn(out_a[e], out_b[e]) * inv_count(b);
-        zero |= (p == 0.0f);
-        job.psd[o] = p;
-        job.de[o] = __log2f(100.0f * p);
+  int ra = 0;
+  while (ra < nrows) {
+    const unsigned g = row0 + ra;
+    const unsigned u = g / job.n_ch;
+    const int ch = static_cast<int>(g - u * job.n_ch);
+    const int seg = min(nrows - ra, static_cast<int>(job.n_ch) - ch);
+    const int n = seg * 5;
+    const int obase = static_cast<int>((u * C::kWindows * job.n_ch + ch) * 5u);
+#pragma unroll 1
+    for (int w = 0; w < C::kWindows; ++w) {
+      const float* const sa = out_a + (w * C::kRows + ra) * 5;
+      const float* const sb = out_b + (w * C::kRows + ra) * 5;
+      float* const gde = job.de + obase + w * win_stride;
+      float* const gpsd = job.psd + obase + w * win_stride;
+#pragma unroll 1
+      for (int i = t; i < n; i += nthreads) {
+        if constexpr (C::kSplit == 1) {
+          gde[i] = sa[i];
+          gpsd[i] = sb[i];
+        } else {
+          const float p = __fadd_rn(sa[i], sb[i]) * inv_count(i % 5);
+          zero |= (p == 0.0f);
+          gpsd[i] = p;
+          gde[i] = __log2f(100.0f * p);
+        }
       }
     }
+    ra += seg;
   }
   return zero;
 }
@@ -260,12 +270,10 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const ring = reinterpret_cast<float*>(smem_raw);
   float* const out_stage = ring + C::kSlots * C::kSlotFloats;               // [group][2][kOutFloats]
-  // Tile geometry (first output index per row, live rows) lives in a ring of 2 kSlots entries indexed by tile
-  // number: the loader may refill tile m's INPUT slot (tile m + kSlots) before the storer has written tile m out,
-  // but it cannot load tile m + 2 kSlots before that (needs tile m + kSlots consumed => its group staged tile
-  // m + kSlots - kGroups => the in-order storer drained tile m + kSlots - 2 kGroups >= m).
-  int* const row_base = reinterpret_cast<int*>(out_stage + C::kGroups * 2 * C::kOutFloats);   // [meta][row]
-  int* const tile_rows = row_base + C::kMeta * C::kRows;                    // [meta]: live rows of the tile
+  // per worker thread: where its window starts inside an input slot, where its 5 results go in the staging tile
+  // and its row -- packed into one word that is re-read from shared memory every tile (the compiler otherwise
+  // rematerialises the lane-map look-up, an indexed constant load with ~1 us of latency, twice per tile).
+  int* const thread_meta = reinterpret_cast<int*>(out_stage + C::kGroups * 2 * C::kOutFloats);   // [kWorkers]
   __shared__ uint64_t full_bar[C::kSlots], empty_bar[C::kSlots], out_full_bar[C::kGroups], out_empty_bar[C::kGroups];
 
   const int tid = threadIdx.x;
@@ -273,7 +281,19 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
   const int n_mine = blockIdx.x < n_tiles ? static_cast<int>((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  auto tile_row0 = [&](int m) { return (blockIdx.x + static_cast<unsigned>(m) * gridDim.x) * C::kRows; };
+  auto tile_nrows = [&](unsigned row0) {
+    const unsigned left = job.total_rows - row0;
+    return static_cast<int>(left < C::kRows ? left : C::kRows);
+  };
 
+  if (tid < C::kWorkers) {
+    const int gt = tid % C::kGroupThreads;
+    int row, w;
+    unit_to_row_window<C>(gt % C::kUnits, row, w);
+    // bits 0..13: window offset in the slot (floats), 14..24: staging index, 25..30: row in tile
+    thread_meta[tid] = (row * C::kRowStride + w * C::kHop) | (((w * C::kRows + row) * 5) << 14) | (row << 25);
+  }
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < C::kSlots; ++s) {
@@ -308,19 +328,12 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           free_slot = mbar_test(&empty_bar[s], ((m / C::kSlots) & 1) ^ 1);
         }
         if (free_slot) {
-          const unsigned row0 = (blockIdx.x + static_cast<unsigned>(m) * gridDim.x) * C::kRows;
-          const unsigned left = job.total_rows - row0;
-          const unsigned nrows = left < C::kRows ? left : C::kRows;
-          const int mi = m % C::kMeta;
-          if (lane == 0) {
-            tile_rows[mi] = static_cast<int>(nrows);
-            mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
-          }
+          const unsigned row0 = tile_row0(m);
+          const unsigned nrows = tile_nrows(row0);
+          if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
           __syncwarp();
           for (unsigned r = lane; r < nrows; r += 32) {
-            int ob;
-            const long long off = row_offset(job, row0 + r, C::kWindows, &ob);
-            row_base[mi * C::kRows + r] = ob;
+            const long long off = row_offset(job, row0 + r, C::kWindows, nullptr);
             bulk_copy_g2s(ring + s * C::kSlotFloats + r * C::kRowStride, job.in + off, C::kRowBytes, &full_bar[s]);
           }
           __syncwarp();
@@ -333,9 +346,9 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           const int mo = next_store;
           const int g = mo % C::kGroups;
           if (mbar_test(&out_full_bar[g], (mo / C::kGroups) & 1)) {
-            const int pm = mo % C::kMeta;
+            const unsigned row0 = tile_row0(mo);
             const float* const out_a = out_stage + g * 2 * C::kOutFloats;
-            store_tile<C>(job, out_a, out_a + C::kOutFloats, row_base + pm * C::kRows, tile_rows[pm], lane, 32);
+            store_tile<C>(job, out_a, out_a + C::kOutFloats, row0, tile_nrows(row0), lane, 32);
             __syncwarp();
             if (lane == 0) mbar_arrive(&out_empty_bar[g]);
             ++next_store;
@@ -350,10 +363,6 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
     const int g = tid / C::kGroupThreads;
     const int gt = tid - g * C::kGroupThreads;
     const int sweep = gt / C::kUnits;                  // 0 when kSplit == 1; warp-uniform (kUnits % 32 == 0)
-    const int unit = gt - sweep * C::kUnits;
-    int row_in_tile, w;
-    unit_to_row_window<C>(unit, row_in_tile, w);
-    const int slot_out = (row_in_tile * C::kWindows + w) * 5;
     float* const out_a = out_stage + g * 2 * C::kOutFloats;
     float* const out_b = out_a + C::kOutFloats;
     float* const out_mine = (C::kSplit == 2 && sweep == 1) ? out_b : out_a;
@@ -361,26 +370,25 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
     for (int m = g; m < n_mine; m += C::kGroups, ++j) {
       const int s = m % C::kSlots;
       mbar_wait(&full_bar[s], (m / C::kSlots) & 1);
-      const bool live = row_in_tile < tile_rows[m % C::kMeta];
-      const float* win = ring + s * C::kSlotFloats + row_in_tile * C::kRowStride + w * C::kHop;
+      const unsigned row0 = tile_row0(m);
+      const int nrows = tile_nrows(row0);
+      const int meta = *reinterpret_cast<volatile int*>(thread_meta + tid);
+      const bool live = (meta >> 25) < nrows;
+      const float* win = ring + s * C::kSlotFloats + (meta & 0x3fff);
       float va[5], vb[5];
       if (live) {
         if constexpr (C::kSplit == 1) {
           float e[5];
           window_band_energy<C::kNi, C::kHann, C::kVec>(win, e);
           if (band_features(e, vb, va) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
-        } else if (sweep == 0) {
-          sweep_even<C::kNi, C::kHann, C::kVec>(win, va);
         } else {
-          sweep_odd<C::kNi, C::kHann, C::kVec>(win, va);
+          sweep_any<C::kNi, C::kHann, C::kVec>(win, sweep, va);
         }
       }
       if constexpr (NORM) {
         // GLMNet raw branch: the staged clip rows leave again as per-channel normalised float32 clips.  Each warp
         // of the group takes every kGroupWarps-th row; a row is 100 float4, stored coalesced.
         static_assert(!NORM || (C::kLoad == 400 && C::kWindows == 7), "normalised clips ride on the 500 ms kernel");
-        const int nrows = tile_rows[m % C::kMeta];
-        const unsigned row0 = (blockIdx.x + static_cast<unsigned>(m) * gridDim.x) * C::kRows;
         for (int r = gt / 32; r < nrows; r += C::kGroupWarps) {
           const unsigned grow = row0 + r;
           const unsigned ch = grow % job.n_ch;
@@ -406,6 +414,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
         mbar_wait(&out_empty_bar[g], (j & 1) ^ 1);         // staging tile drained by the storer warp
       }
       if (live) {
+        const int slot_out = (*reinterpret_cast<volatile int*>(thread_meta + tid) >> 14) & 0x7ff;
 #pragma unroll
         for (int b = 0; b < 5; ++b) {
           out_mine[slot_out + b] = va[b];
@@ -414,9 +423,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       }
       if constexpr (C::kGroupStore) {
         group_barrier(1 + g, C::kGroupThreads);            // all of the group's results are staged
-        const int pm = m % C::kMeta;
-        if (store_tile<C>(job, out_a, out_b, row_base + pm * C::kRows, tile_rows[pm], gt, C::kGroupThreads) &&
-            job.status != nullptr)
+        if (store_tile<C>(job, out_a, out_b, row0, nrows, gt, C::kGroupThreads) && job.status != nullptr)
           atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
       } else {
         __syncwarp();
