@@ -187,10 +187,11 @@ __device__ __forceinline__ bool band_features(const float (&e)[5], float (&psd)[
 // thread `t` of `nthreads` taking consecutive addresses.  A tile spans 1 + (kRows - 1) / n_ch clips at most.
 // kSplit == 2: the two sweeps' partials are added and turned into (psd, de) here.
 // Returns true if a zero-power band was seen (kSplit == 2 only).
-template <class C>
+template <class C, int NT>
 __device__ __forceinline__ bool store_tile(const Job& job, const float* out_a, const float* out_b, unsigned row0,
-                                           int nrows, int t, int nthreads)
+                                           int nrows, int t)
 {
+  constexpr int kIter = (C::kRows * 5 + NT - 1) / NT;      // a run is at most 5 kRows floats
   const int win_stride = static_cast<int>(job.n_ch) * 5;
   bool zero = false;
   int ra = 0;
@@ -201,24 +202,37 @@ __device__ __forceinline__ bool store_tile(const Job& job, const float* out_a, c
     const int seg = min(nrows - ra, static_cast<int>(job.n_ch) - ch);
     const int n = seg * 5;
     const int obase = static_cast<int>((u * C::kWindows * job.n_ch + ch) * 5u);
+    const float* sa = out_a + ra * 5 + t;
+    const float* sb = out_b + ra * 5 + t;
+    float* gde = job.de + obase + t;
+    float* gpsd = job.psd + obase + t;
 #pragma unroll 1
     for (int w = 0; w < C::kWindows; ++w) {
-      const float* const sa = out_a + (w * C::kRows + ra) * 5;
-      const float* const sb = out_b + (w * C::kRows + ra) * 5;
-      float* const gde = job.de + obase + w * win_stride;
-      float* const gpsd = job.psd + obase + w * win_stride;
-#pragma unroll 1
-      for (int i = t; i < n; i += nthreads) {
-        if constexpr (C::kSplit == 1) {
-          gde[i] = sa[i];
-          gpsd[i] = sb[i];
-        } else {
-          const float p = __fadd_rn(sa[i], sb[i]) * inv_count(i % 5);
-          zero |= (p == 0.0f);
-          gpsd[i] = p;
-          gde[i] = __log2f(100.0f * p);
+      // all loads first, then all stores: the copy is latency-bound on one warp otherwise
+      float va[kIter], vb[kIter];
+#pragma unroll
+      for (int k = 0; k < kIter; ++k)
+        if (t + k * NT < n) {
+          va[k] = sa[k * NT];
+          vb[k] = sb[k * NT];
         }
-      }
+#pragma unroll
+      for (int k = 0; k < kIter; ++k)
+        if (t + k * NT < n) {
+          if constexpr (C::kSplit == 1) {
+            gde[k * NT] = va[k];
+            gpsd[k * NT] = vb[k];
+          } else {
+            const float p = __fadd_rn(va[k], vb[k]) * inv_count((t + k * NT) % 5);
+            zero |= (p == 0.0f);
+            gpsd[k * NT] = p;
+            gde[k * NT] = __log2f(100.0f * p);
+          }
+        }
+      sa += C::kRows * 5;
+      sb += C::kRows * 5;
+      gde += win_stride;
+      gpsd += win_stride;
     }
     ra += seg;
   }
@@ -348,7 +362,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           if (mbar_test(&out_full_bar[g], (mo / C::kGroups) & 1)) {
             const unsigned row0 = tile_row0(mo);
             const float* const out_a = out_stage + g * 2 * C::kOutFloats;
-            store_tile<C>(job, out_a, out_a + C::kOutFloats, row0, tile_nrows(row0), lane, 32);
+            store_tile<C, 32>(job, out_a, out_a + C::kOutFloats, row0, tile_nrows(row0), lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(&out_empty_bar[g]);
             ++next_store;
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       }
       if constexpr (C::kGroupStore) {
         group_barrier(1 + g, C::kGroupThreads);            // all of the group's results are staged
-        if (store_tile<C>(job, out_a, out_b, row0, nrows, gt, C::kGroupThreads) && job.status != nullptr)
+        if (store_tile<C, C::kGroupThreads>(job, out_a, out_b, row0, nrows, gt) && job.status != nullptr)
           atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
       } else {
         __syncwarp();
