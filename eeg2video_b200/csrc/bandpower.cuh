@@ -285,10 +285,10 @@ using Group = std::conditional_t<NI == 4, Group4<HANN, RHO, VEC>, Group8<HANN, R
 // to ~25 KB.  It also keeps the compiler from merging the two sweeps' loads and radix-8 partial sums (which cost
 // ~100 extra live registers).
 template <int NI, int HANN, int VEC>
-EEGFE_FN void sweep_any(const float* win, int sweep, float (&part)[5])
+EEGFE_FN void sweep_any(const float* win, int sweep, const float (&carry)[5], float (&part)[5])
 {
   cf acc[5];
-  static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_make(0.f, 0.f); });
+  static_for<0, 5>([&](auto b_) { acc[decltype(b_)::value] = c_make(carry[decltype(b_)::value], 0.f); });
   cf p[25], q[25];
   if (sweep == 0) {
     static_for<0, 25>([&](auto rho_) {
@@ -319,20 +319,32 @@ EEGFE_FN void sweep_any(const float* win, int sweep, float (&part)[5])
   });
 }
 
+// Both sweeps in one thread.
+//  * NI = 8 (1 s / 2 s windows): E_b = part_even[b] + part_odd[b], the same additions the split kernels make, so the
+//    one-thread and two-warp paths agree bit for bit.
+//  * NI = 4 (500 ms windows; never split): the odd sweep's accumulators START from the even sweep's partial sums
+//    (sweep 0 is always the even one), so nothing but five floats crosses the loop back-edge -- holding part_even
+//    in registers through the second sweep cost five spills whose reloads sat exposed at the end of every window.
 template <int NI, int HANN, int VEC>
 EEGFE_FN void window_band_energy(const float* win, float (&energy)[5])
 {
+  float carry[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float pe[5];
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
   for (int sweep = EEGFE_OPAQUE_ZERO(); sweep < 2; ++sweep) {
     float part[5];
-    sweep_any<NI, HANN, VEC>(win, sweep, part);
+    sweep_any<NI, HANN, VEC>(win, sweep, carry, part);
     static_for<0, 5>([&](auto b_) {
       constexpr int b = decltype(b_)::value;
-      if (sweep == 0) pe[b] = part[b];
-      else energy[b] = f_add(pe[b], part[b]);
+      if constexpr (NI == 4) {
+        carry[b] = part[b];
+        energy[b] = part[b];
+      } else {
+        if (sweep == 0) pe[b] = part[b];
+        else energy[b] = f_add(pe[b], part[b]);
+      }
     });
   }
 }

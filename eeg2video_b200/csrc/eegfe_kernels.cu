@@ -261,6 +261,10 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
   }
 }
 
+}  // namespace eegfe
+#include "eegfe_stream.cuh"
+namespace eegfe {
+
 // ---------------------------------------------------------------------------------------------------------------
 // the fused kernel (rows 16-byte aligned): warp-specialised, no block-wide barrier in the steady state
 //
@@ -396,7 +400,8 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           window_band_energy<C::kNi, C::kHann, C::kVec>(win, e);
           if (band_features(e, vb, va) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
         } else {
-          sweep_any<C::kNi, C::kHann, C::kVec>(win, sweep, va);
+          const float zero5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          sweep_any<C::kNi, C::kHann, C::kVec>(win, sweep, zero5, va);
         }
       }
       if constexpr (NORM) {
@@ -609,11 +614,41 @@ static int sm_count()
   return n;
 }
 
+// 500 ms mode, 16-byte aligned rows: the streaming kernel (eegfe_stream.cuh), one CTA of 16 warps per SM.
+static int launch_stream(const Job& job, cudaStream_t stream)
+{
+  if (job.total_rows == 0) return 0;
+  const unsigned n_tiles = (job.total_rows + StreamCfg::kRows - 1) / StreamCfg::kRows;
+  unsigned grid = static_cast<unsigned>(sm_count());
+  if (grid > n_tiles) grid = n_tiles;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(de_psd_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         StreamCfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(de_psd_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               StreamCfg::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  if (job.norm_out != nullptr)
+    de_psd_stream_kernel<true><<<grid, StreamCfg::kThreads, StreamCfg::kSmemBytes, stream>>>(job);
+  else
+    de_psd_stream_kernel<false><<<grid, StreamCfg::kThreads, StreamCfg::kSmemBytes, stream>>>(job);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
 // One launch over `job.total_rows` rows (< 2^31, output indices < 2^31: guaranteed by run_units()).
 template <class C>
 static int launch(const Job& job, bool aligned16, cudaStream_t stream)
 {
   if (job.total_rows == 0) return 0;
+#ifndef EEGFE_500MS_RING      // (A/B builds only: -DEEGFE_500MS_RING keeps the 500 ms mode on the ring kernel)
+  if constexpr (C::kLoad == 400 && C::kWindows == 7) {
+    if (aligned16) return launch_stream(job, stream);
+  }
+#endif
   const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (aligned16) {
     unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
@@ -953,7 +988,11 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 {
   int g = 0, b = 0, s = 0, r = 0;
   switch (mode) {
+#ifndef EEGFE_500MS_RING
+    case EEGFE_MODE_500MS: g = 1; b = StreamCfg::kThreads; s = StreamCfg::kSmemBytes; r = StreamCfg::kRows; break;
+#else
     case EEGFE_MODE_500MS: g = CfgSliding500::kCtasPerSm; b = CfgSliding500::kThreads; s = CfgSliding500::kSmemBytes; r = CfgSliding500::kRows; break;
+#endif
     case EEGFE_MODE_1S: g = CfgOneSec::kCtasPerSm; b = CfgOneSec::kThreads; s = CfgOneSec::kSmemBytes; r = CfgOneSec::kRows; break;
     case EEGFE_MODE_2S: g = CfgTwoSec::kCtasPerSm; b = CfgTwoSec::kThreads; s = CfgTwoSec::kSmemBytes; r = CfgTwoSec::kRows; break;
     default: return EEGFE_EINVAL;

@@ -1,0 +1,259 @@
+// Streaming form of the fused 500 ms kernel: 16 identical warps per SM, no specialised producer / storer warp.
+//
+// Why.  The ring kernel (de_psd_kernel) runs 2 CTAs x (7 worker warps + 1 producer warp) per SM at 128 registers.
+// Warps land on the four SM sub-partitions round-robin, so three sub-partitions carry 4 worker warps and the
+// fourth carries 2 workers + the 2 producers: the FP32 pipe of that sub-partition idles half of the time and the
+// kernel tops out at 14/16 of the pipe (ncu: 74 %).  A 17th warp does not fit the register file.  Here every warp
+// is a worker (16 x 32 x 128 registers = the whole file) and the two serial duties -- issuing the TMA copies of the
+// next tile, writing a finished tile's features to HBM -- fall to whichever warp happens to finish a tile last.
+//
+// Structure.  A CTA owns tiles t = 0, 1, ... (global tile blockIdx.x + t * gridDim.x) of 16 rows; tile t lives in
+// ring slot t % S.  A tile holds 16 rows x 7 windows = 112 channel-windows = 7 HALF-PASSES of 16 lanes (the lane
+// map of eegfe_tables.h makes each half-warp's LDS.64 pattern conflict-free, the 7th 2-way).  The CTA's work is
+// the stream of half-passes h = 0 .. 7 * n_tiles - 1; warps draw PASSES (two consecutive half-passes) from a
+// shared counter, so a pass may straddle two tiles and no lane ever idles on a tile boundary.
+//
+//   per pass:   wait full[slot]                         (TMA bytes landed; mbarrier transaction count)
+//               one channel-window per lane, register FFT (bandpower.cuh)
+//               consumed[slot] += half-passes           -> the warp that completes the tile re-arms full[slot] and
+//                                                          issues the 16 bulk copies of tile t + S into the slot
+//               wait drained[slot] >= generation        (staging rows of the slot's previous tile written out;
+//                                                          true long before in practice)
+//               stage 5 DE + 5 PSD per lane             [window][row][band]
+//               staged[slot] += half-passes             -> the warp that completes the tile copies the staged tile
+//                                                          to HBM (linear runs, see store_tile) and bumps drained
+//
+// No block-wide or group barrier exists after the prologue.  Progress: the oldest unfinished pass only ever waits
+// for copies / copy-outs triggered by strictly older passes.
+#pragma once
+
+namespace eegfe {
+
+struct StreamCfg {
+  static constexpr int kRows = 16;            // rows per tile
+  static constexpr int kWindows = 7;
+  static constexpr int kHop = 50;
+  static constexpr int kLoad = 400;
+  static constexpr int kRowStride = 404;      // floats; bank skew, see Cfg
+  static constexpr int kRowBytes = kLoad * 4;
+  static constexpr int kSlots = 7;
+  static constexpr int kWarps = 16;
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kUnits = kRows * kWindows;          // 112
+  static constexpr int kHalfPasses = kUnits / 16;          // 7
+  static constexpr int kSlotFloats = kRows * kRowStride;
+  static constexpr int kOutFloats = kUnits * 5;            // per staging array
+  static constexpr int kSplit = 1;                         // store_tile: staged values are final (de, psd)
+  static constexpr int kSmemBytes = (kSlots * (kSlotFloats + 2 * kOutFloats) + kUnits) * 4;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
+};
+
+__constant__ unsigned char c_lane_map_500_r16[112] = {EEGFE_LANE_MAP_500_R16};
+
+__device__ __forceinline__ unsigned atom_add_acq_rel_smem(unsigned* p, unsigned v)
+{
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned ld_acquire_smem(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_smem(unsigned* p, unsigned v)
+{
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#ifndef EEGFE_STREAM_DUTY
+#define EEGFE_STREAM_DUTY __forceinline__
+#endif
+// The serial duties (once per tile).  Inlined: as real calls they cost 4 % (uniform registers holding the twiddle
+// constants cannot stay live across a call and are re-materialised every pass); -DEEGFE_STREAM_DUTY=__noinline__
+// builds the out-of-line form for comparison.
+
+// whole warp: re-arm `bar` and issue one bulk copy per row of the tile starting at global row `row0`
+__device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot, uint64_t* bar, unsigned row0, int nrows)
+{
+  const Job& job = *jobp;
+  const int lane = threadIdx.x & 31;
+  fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy refill
+  if (lane == 0) mbar_arrive_expect_tx(bar, nrows * StreamCfg::kRowBytes);
+  __syncwarp();
+  if (lane < nrows) {
+    const long long off = row_offset(job, row0 + lane, StreamCfg::kWindows, nullptr);
+    bulk_copy_g2s(slot + lane * StreamCfg::kRowStride, job.in + off, StreamCfg::kRowBytes, bar);
+  }
+  __syncwarp();
+}
+
+// whole warp: staged tile -> HBM
+__device__ EEGFE_STREAM_DUTY void stream_store_tile(const Job* jobp, const float* out_a, unsigned row0, int nrows)
+{
+  store_tile<StreamCfg, 32>(*jobp, out_a, out_a + StreamCfg::kOutFloats, row0, nrows, threadIdx.x & 31);
+  __syncwarp();
+}
+
+// whole warp: GLMNet raw branch -- the clip rows of a consumed tile leave again as per-channel normalised clips
+__device__ EEGFE_STREAM_DUTY void stream_store_norm(const Job* jobp, const float* slot, unsigned row0, int nrows)
+{
+  const Job& job = *jobp;
+  const int lane = threadIdx.x & 31;
+  for (int r = 0; r < nrows; ++r) {
+    const unsigned grow = row0 + r;
+    const unsigned ch = grow % job.n_ch;
+    const float sc = __ldg(job.norm_scale + ch), sh = __ldg(job.norm_shift + ch);
+    const float4* src = reinterpret_cast<const float4*>(slot + r * StreamCfg::kRowStride);
+    float4* dst = reinterpret_cast<float4*>(job.norm_out + (job.norm_row0 + grow) * 400);
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (lane + 32 * i < 100) v[i] = src[lane + 32 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (lane + 32 * i < 100) {
+        v[i].x = fmaf(v[i].x, sc, sh);
+        v[i].y = fmaf(v[i].y, sc, sh);
+        v[i].z = fmaf(v[i].z, sc, sh);
+        v[i].w = fmaf(v[i].w, sc, sh);
+        dst[lane + 32 * i] = v[i];
+      }
+  }
+  __syncwarp();
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(const __grid_constant__ Job job)
+{
+  using C = StreamCfg;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* const ring = reinterpret_cast<float*>(smem_raw);                     // [slot][row][kRowStride]
+  float* const stage = ring + C::kSlots * C::kSlotFloats;                      // [slot][de | psd][window][row][band]
+  int* const unit_meta = reinterpret_cast<int*>(stage + C::kSlots * 2 * C::kOutFloats);   // [kUnits]
+  __shared__ uint64_t full_bar[C::kSlots];
+  __shared__ unsigned consumed[C::kSlots], staged[C::kSlots], drained[C::kSlots];
+  __shared__ unsigned next_pass;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
+  const unsigned n_mine = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const unsigned n_half = n_mine * C::kHalfPasses;
+  auto tile_row0 = [&](unsigned t) { return (blockIdx.x + t * gridDim.x) * C::kRows; };
+  auto tile_nrows = [&](unsigned row0) {
+    const unsigned left = job.total_rows - row0;
+    return static_cast<int>(left < C::kRows ? left : C::kRows);
+  };
+
+  if (tid < C::kUnits) {
+    const int code = c_lane_map_500_r16[tid];
+    const int row = code >> 3, w = code & 7;
+    // bits 0..13: window offset in the slot (floats), 14..24: staging index, 25..30: row in tile
+    unit_meta[tid] = (row * C::kRowStride + w * C::kHop) | (((w * C::kRows + row) * 5) << 14) | (row << 25);
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < C::kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      consumed[s] = 0;
+      staged[s] = 0;
+      drained[s] = 0;
+    }
+    next_pass = 0;
+    mbar_fence_init();
+  }
+  __syncthreads();
+  {
+    const unsigned w = tid >> 5;
+    if (w < C::kSlots && w < n_mine) {
+      const unsigned row0 = tile_row0(w);
+      stream_load_tile(&job, ring + w * C::kSlotFloats, &full_bar[w], row0, tile_nrows(row0));
+    }
+  }
+
+  for (;;) {
+    unsigned pass = 0;
+    if (lane == 0) pass = atomicAdd(&next_pass, 1u);
+    pass = __shfl_sync(0xffffffffu, pass, 0);
+    if (2 * pass >= n_half) break;
+    // lane -> (tile, half-pass in tile, slot, generation, unit geometry); evaluated twice per pass (before the FFT
+    // and again after it) so that nothing but `pass` and the ten results stays live across the FFT
+    unsigned t, gen;
+    int s, meta;
+    bool valid;
+    auto locate = [&]() {
+      const unsigned h = 2 * pass + (lane >> 4);
+      valid = h < n_half;                                // the very last pass of a CTA may be half empty
+      const unsigned hh = valid ? h : n_half - 1;
+      t = hh / C::kHalfPasses;
+      s = static_cast<int>(t % C::kSlots);
+      gen = t / C::kSlots;
+      meta = *reinterpret_cast<volatile int*>(unit_meta + static_cast<int>(hh - t * C::kHalfPasses) * 16 + (lane & 15));
+    };
+    float de[5], psd[5];
+    bool live;
+    {
+      locate();
+      const unsigned t0 = __shfl_sync(0xffffffffu, t, 0), t1 = __shfl_sync(0xffffffffu, t, 16);
+      mbar_wait(&full_bar[t0 % C::kSlots], (t0 / C::kSlots) & 1);
+      if (t1 != t0) mbar_wait(&full_bar[t1 % C::kSlots], (t1 / C::kSlots) & 1);
+      live = valid && (meta >> 25) < tile_nrows(tile_row0(t));
+      if (live) {
+        float e[5];
+        window_band_energy<4, kHannHalfSec, 2>(ring + s * C::kSlotFloats + (meta & 0x3fff), e);
+        if (band_features(e, psd, de) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
+      }
+    }
+    asm volatile("" : "+r"(pass));                        // everything below is recomputed from `pass` alone
+    locate();
+    if (live) {
+      // staging rows of the slot's previous tile must have been written out (true long before, in practice)
+      while (ld_acquire_smem(&drained[s]) < gen) __nanosleep(32);
+      float* const sd = stage + s * 2 * C::kOutFloats + ((meta >> 14) & 0x7ff);
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        sd[b] = de[b];
+        sd[C::kOutFloats + b] = psd[b];
+      }
+    }
+    __syncwarp();
+    // ---- retire: per tile touched by this pass (one or two), count this warp's half-passes in; whoever completes
+    //      the count refills the input slot, whoever completes the staging count writes the tile out ----
+    const unsigned h0 = 2 * pass;
+    const unsigned t0 = h0 / C::kHalfPasses;
+    const unsigned t1 = (h0 + 1 < n_half) ? (h0 + 1) / C::kHalfPasses : t0;
+    const unsigned halves0 = (t1 != t0) ? 1u : ((h0 + 1 < n_half) ? 2u : 1u);   // valid half-passes in tile t0
+#pragma unroll 1
+    for (unsigned tk = t0; tk <= t1; ++tk) {
+      const unsigned cnt = tk == t0 ? halves0 : 1u;
+      const int sk = static_cast<int>(tk % C::kSlots);
+      const unsigned done = C::kHalfPasses * (tk / C::kSlots + 1);
+      unsigned last = 0;
+      if (lane == 0) {
+        last = (atom_add_acq_rel_smem(&consumed[sk], cnt) + cnt == done) ? 1u : 0u;
+        last |= (atom_add_acq_rel_smem(&staged[sk], cnt) + cnt == done) ? 2u : 0u;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last & 1u) {
+        if constexpr (NORM) {
+          const unsigned r0 = tile_row0(tk);
+          stream_store_norm(&job, ring + sk * C::kSlotFloats, r0, tile_nrows(r0));
+        }
+        if (tk + C::kSlots < n_mine) {
+          const unsigned r0 = tile_row0(tk + C::kSlots);
+          stream_load_tile(&job, ring + sk * C::kSlotFloats, &full_bar[sk], r0, tile_nrows(r0));
+        }
+      }
+      if (last & 2u) {
+        const unsigned r0 = tile_row0(tk);
+        stream_store_tile(&job, stage + sk * 2 * C::kOutFloats, r0, tile_nrows(r0));
+        if (lane == 0) st_release_smem(&drained[sk], tk / C::kSlots + 1);
+      }
+    }
+  }
+}
+
+}  // namespace eegfe
