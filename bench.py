@@ -29,6 +29,11 @@ if ROOT not in sys.path:
 CW_PER_SUBJECT = {"500ms": 7 * 40 * 5 * 7 * 62, "1s": 7 * 40 * 5 * 2 * 62, "2s": 7 * 40 * 5 * 62}
 # algorithmic bytes per channel-window (SURVEY.md 8d / BASELINE.md 4): live input samples + 40 B of features
 BYTES_PER_CW = {"500ms": 1600.0 / 7 + 40, "1s": 840.0, "2s": 840.0}
+# fp32 lane-operations per channel-window of the pruned FFT + band power (counted from the SASS of the kernel:
+# 2 x packed f32x2 instructions + scalar FP instructions per window)
+FP32_LANE_OPS_PER_CW = {"500ms": 2420.0, "1s": 2660.0, "2s": 2660.0}
+KERNEL_NAME = {"500ms": "eegfe::de_psd_stream_kernel (500 ms sliding, fused segmentation)",
+               "1s": "eegfe::de_psd_kernel<CfgOneSec>", "2s": "eegfe::de_psd_kernel<CfgTwoSec>"}
 _REAL_STDOUT = None
 
 
@@ -345,6 +350,35 @@ def run_gpu_arm(args):
         elapsed_ms = float(t.item())
     value = world * cw_step_gpu * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- the other two analysis modes over the same resident batch (kernel only; informative, rank 0) ----
+    other_modes = {}
+    if rank == 0 and not args.skip_other_modes:
+        for om in ("500ms", "1s", "2s"):
+            if om == mode:
+                continue
+            om_id = frontend.MODES[om]
+            o_de = torch.empty((S * 7 * 200, ops.WINDOWS_PER_CLIP[om_id], 62, 5), dtype=torch.float32, device=dev)
+            o_psd = torch.empty_like(o_de)
+
+            def o_step():
+                _lib.check(lib.eegfe_de_psd_from_raw(raw.data_ptr(), raw.shape[0], 62, 104000, raw.stride(0),
+                                                     raw.stride(1), om_id, o_de.data_ptr(), o_psd.data_ptr(),
+                                                     status.data_ptr(), stream.cuda_stream))
+            for _ in range(3):
+                o_step()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record(stream)
+            for _ in range(args.steps):
+                o_step()
+            o1.record(stream)
+            torch.cuda.synchronize()
+            o_ms = o0.elapsed_time(o1) / args.steps
+            o_cw = S * CW_PER_SUBJECT[om]
+            o_gbs = o_cw * BYTES_PER_CW[om] / (o_ms * 1e-3) / 1e9
+            other_modes[om] = {"value": o_cw / (o_ms * 1e-3), "unit": UNIT, "kernel_ms": o_ms,
+                               "hbm_gbs": o_gbs, "hbm_frac": o_gbs / measured_peaks()[0], "kernel": KERNEL_NAME[om]}
+            del o_de, o_psd
+
     # ---- end to end: pinned host recordings -> H2D -> fused kernel -> D2H of the features, every step ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     pipe = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode)
@@ -402,11 +436,17 @@ def run_gpu_arm(args):
         traffic = profiled_traffic(mode)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None if traffic is None else traffic["dram_bytes_per_cw"] * cw_step_gpu,
-                    "peak_source": peak_src, "kernel": "eegfe::de_psd_kernel<Cfg500ms>" if mode == "500ms" else
-                    "eegfe::de_psd_kernel", "kernel_ms": kernel_ms,
+                    "peak_source": peak_src, "kernel": KERNEL_NAME[mode], "kernel_ms": kernel_ms,
                     "algorithmic_bytes_per_channel_window": BYTES_PER_CW[mode],
-                    "note": "500 ms mode is bounded by the FP32 pipe, not HBM (DESIGN.md 'Rooflines')"
+                    "note": "500 ms mode is bounded by the FP32 pipe, not HBM (DESIGN.md 'Rooflines'); see 'fp32_pipe'"
                     if mode == "500ms" else ""}
+        # the CUDA-core FP32 pipe is what actually bounds the 500 ms kernel: 128 lanes/clk/SM at the clock seen under load
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        fp_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
+        fp_ach = cw_step_gpu * FP32_LANE_OPS_PER_CW[mode] / (kernel_ms * 1e-3) / 1e12
+        fp32_pipe = {"achieved": fp_ach, "peak": fp_peak, "unit": "T fp32 lane-op/s (an FMA counts once)",
+                     "frac": fp_ach / fp_peak, "lane_ops_per_channel_window": FP32_LANE_OPS_PER_CW[mode],
+                     "peak_source": f"148 SMs x 128 lanes x {sm_mhz:.0f} MHz (median SM clock sampled during the run)"}
         cpu = None
         if not args.skip_cpu_baseline and world == 1:
             arm = CpuArm(mode)
@@ -427,7 +467,8 @@ def run_gpu_arm(args):
                     "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
                             "D2H of DE+PSD, 3 streams) -> pinned host features"},
             "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "fp32_pipe": fp32_pipe, "other_modes": other_modes, "cpu_baseline": cpu,
+            "parity": parity,
         }
         if gather:
             line["gather"] = gather
@@ -451,6 +492,7 @@ def main():
     ap.add_argument("--clock-probe-s", type=float, default=1.5)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--skip-other-modes", action="store_true")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":

@@ -274,6 +274,34 @@ def test_leading_axes_and_odd_channel_counts():
     assert_features_close(de[0].cpu().numpy(), psd[0].cpu().numpy(), de_ref, psd_ref)
 
 
+@pytest.mark.parametrize("n_clips,n_ch", ((1, 1), (1, 3), (2, 5), (3, 16), (5, 17), (7, 31), (1, 62), (9, 62), (50, 64),
+                                          (33, 7), (200, 2)))
+def test_streaming_kernel_ragged_tiles(n_clips, n_ch):
+    """500 ms streaming kernel (16-row tiles, 7 half-passes per tile, passes straddling tiles): row counts that
+    leave the last tile partial, odd numbers of half-passes per CTA, tiles spanning several clips (n_ch < 16)
+    and tiles cut by a clip boundary -- every channel-window against the float64 closed form."""
+    rng = np.random.default_rng(1000 * n_clips + n_ch)
+    clips = (30 * rng.standard_normal((n_clips, n_ch, 400)) + rng.uniform(-50, 50, (n_clips, n_ch, 1))).astype(np.float32)
+    de, psd = frontend.de_psd_from_clips(torch.from_numpy(clips).to(DEV), "500ms")
+    assert tuple(de.shape) == (n_clips, 7, n_ch, 5)
+    wins = np.stack([clips[..., 50 * w:50 * w + 100] for w in range(7)], axis=1)        # (n, 7, ch, 100)
+    de_ref, psd_ref = oracle.de_psd_closed_form(wins, 200, 0.5)
+    assert_features_close(de.cpu().numpy(), psd.cpu().numpy(), de_ref, psd_ref)
+
+
+def test_streaming_kernel_many_tiles_per_cta():
+    """More tiles than ring slots on every SM (2 subjects = 10850 tiles / 148 SMs = 73 per CTA, 10 generations of
+    the 7-slot ring), twice in a row on the same buffers: slot recycling, staging drain flags, determinism."""
+    raw = synth.synth_blocks(14, 9, device=DEV)
+    a = frontend.de_psd_from_raw(raw, "500ms")
+    b = frontend.de_psd_from_raw(raw, "500ms")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    clips = frontend.segment_clips(raw[3])
+    wins = frontend.sliding_windows(clips)                                              # (40,5,7,62,100)
+    de_w, psd_w = frontend.de_psd_windows(wins)                                         # ring kernel, pre-cut windows
+    assert torch.equal(a[0][3], de_w) and torch.equal(a[1][3], psd_w)
+
+
 def test_unaligned_block_length_uses_fallback_loader():
     """T = 104001: rows are only 4-byte aligned, so TMA bulk copies are impossible; same results required."""
     raw = synth.synth_blocks(1, 5, device=DEV, channels=62, block_len=104001)
