@@ -379,6 +379,41 @@ def run_gpu_arm(args):
                                "hbm_gbs": o_gbs, "hbm_frac": o_gbs / measured_peaks()[0], "kernel": KERNEL_NAME[om]}
             del o_de, o_psd
 
+    # ---- next row: GLMNet input build = normalised 2 s clips + 500 ms features in one pass ----
+    next_rows = {}
+    if rank == 0 and not args.skip_other_modes:
+        from eeg2video_b200 import glmnet_inputs
+        mean, std = glmnet_inputs.channel_stats(raw, None)
+        scale = (1.0 / std).to(torch.float32).contiguous()
+        shift = (-mean / std).to(torch.float32).contiguous()
+        g_clips = torch.empty((S * 7 * 200, 62, 400), dtype=torch.float32, device=dev)
+        g_de = torch.empty((S * 7 * 200, 7, 62, 5), dtype=torch.float32, device=dev)
+        g_psd = torch.empty_like(g_de)
+
+        def g_step():
+            _lib.check(lib.eegfe_glmnet_inputs_from_raw(raw.data_ptr(), raw.shape[0], 62, 104000, raw.stride(0),
+                                                        raw.stride(1), scale.data_ptr(), shift.data_ptr(),
+                                                        g_clips.data_ptr(), g_de.data_ptr(), g_psd.data_ptr(),
+                                                        status.data_ptr(), stream.cuda_stream))
+        for _ in range(3):
+            g_step()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            g_step()
+        g1.record(stream)
+        torch.cuda.synchronize()
+        g_ms = g0.elapsed_time(g1) / args.steps
+        rows = S * 7 * 200 * 62                                   # channel-clips
+        g_bytes = rows * (1600 + 1600 + 7 * 40)                   # clip in, normalised clip out, 7 x (DE+PSD) out
+        next_rows["glmnet_inputs_from_raw"] = {
+            "value": rows * 7 / (g_ms * 1e-3), "unit": UNIT, "kernel_ms": g_ms,
+            "algorithmic_bytes_per_channel_clip": 3480, "hbm_gbs": g_bytes / (g_ms * 1e-3) / 1e9,
+            "hbm_frac": g_bytes / (g_ms * 1e-3) / 1e9 / measured_peaks()[0],
+            "kernel": "eegfe::de_psd_stream_kernel<NORM> (500 ms features + per-channel normalised clips, one pass)",
+            "features_identical_to_plain_kernel": bool(torch.equal(g_de, de_buf) and torch.equal(g_psd, psd_buf))}
+        del g_clips, g_de, g_psd
+
     # ---- end to end: pinned host recordings -> H2D -> fused kernel -> D2H of the features, every step ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     pipe = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode)
@@ -467,7 +502,8 @@ def run_gpu_arm(args):
                     "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
                             "D2H of DE+PSD, 3 streams) -> pinned host features"},
             "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),
-            "roofline": roofline, "fp32_pipe": fp32_pipe, "other_modes": other_modes, "cpu_baseline": cpu,
+            "roofline": roofline, "fp32_pipe": fp32_pipe, "other_modes": other_modes, "next_rows": next_rows,
+            "cpu_baseline": cpu,
             "parity": parity,
         }
         if gather:

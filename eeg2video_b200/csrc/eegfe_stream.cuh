@@ -97,32 +97,32 @@ __device__ EEGFE_STREAM_DUTY void stream_store_tile(const Job* jobp, const float
   __syncwarp();
 }
 
-// whole warp: GLMNet raw branch -- the clip rows of a consumed tile leave again as per-channel normalised clips
-__device__ EEGFE_STREAM_DUTY void stream_store_norm(const Job* jobp, const float* slot, unsigned row0, int nrows)
+// GLMNet raw branch: half-pass q of a tile writes rows q, q + 7, q + 14 of the tile out again as per-channel normalised
+// clips (x * scale[ch] + shift[ch]), 16 lanes x float4 per row -- spread over all passes instead of one warp per tile
+// (as a last-reader duty it cost 40 %: 25.6 KB copied by a single warp per tile).
+__device__ __forceinline__ void stream_store_norm_rows(const Job& job, const float* slot, unsigned row0, int nrows, int q,
+                                                       int lane16)
 {
-  const Job& job = *jobp;
-  const int lane = threadIdx.x & 31;
-  for (int r = 0; r < nrows; ++r) {
+  for (int r = q; r < nrows; r += StreamCfg::kHalfPasses) {
     const unsigned grow = row0 + r;
     const unsigned ch = grow % job.n_ch;
     const float sc = __ldg(job.norm_scale + ch), sh = __ldg(job.norm_shift + ch);
     const float4* src = reinterpret_cast<const float4*>(slot + r * StreamCfg::kRowStride);
     float4* dst = reinterpret_cast<float4*>(job.norm_out + (job.norm_row0 + grow) * 400);
-    float4 v[4];
+    float4 v[7];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (lane + 32 * i < 100) v[i] = src[lane + 32 * i];
+    for (int i = 0; i < 7; ++i)
+      if (lane16 + 16 * i < 100) v[i] = src[lane16 + 16 * i];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (lane + 32 * i < 100) {
+    for (int i = 0; i < 7; ++i)
+      if (lane16 + 16 * i < 100) {
         v[i].x = fmaf(v[i].x, sc, sh);
         v[i].y = fmaf(v[i].y, sc, sh);
         v[i].z = fmaf(v[i].z, sc, sh);
         v[i].w = fmaf(v[i].w, sc, sh);
-        dst[lane + 32 * i] = v[i];
+        dst[lane16 + 16 * i] = v[i];
       }
   }
-  __syncwarp();
 }
 
 template <bool NORM>
@@ -201,6 +201,16 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
       mbar_wait(&full_bar[t0 % C::kSlots], (t0 / C::kSlots) & 1);
       if (t1 != t0) mbar_wait(&full_bar[t1 % C::kSlots], (t1 / C::kSlots) & 1);
       live = valid && (meta >> 25) < tile_nrows(tile_row0(t));
+      if constexpr (NORM) {
+        if (valid) {
+          const unsigned r0 = tile_row0(t);
+          stream_store_norm_rows(job, ring + s * C::kSlotFloats, r0, tile_nrows(r0),
+                                 static_cast<int>((2 * pass + (lane >> 4)) - t * C::kHalfPasses), lane & 15);
+        }
+        __syncwarp();
+        asm volatile("" : "+r"(pass));
+        locate();
+      }
       if (live) {
         float e[5];
         window_band_energy<4, kHannHalfSec, 2>(ring + s * C::kSlotFloats + (meta & 0x3fff), e);
@@ -238,10 +248,6 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
       }
       last = __shfl_sync(0xffffffffu, last, 0);
       if (last & 1u) {
-        if constexpr (NORM) {
-          const unsigned r0 = tile_row0(tk);
-          stream_store_norm(&job, ring + sk * C::kSlotFloats, r0, tile_nrows(r0));
-        }
         if (tk + C::kSlots < n_mine) {
           const unsigned r0 = tile_row0(tk + C::kSlots);
           stream_load_tile(&job, ring + sk * C::kSlotFloats, &full_bar[sk], r0, tile_nrows(r0));
