@@ -414,6 +414,41 @@ def run_gpu_arm(args):
             "features_identical_to_plain_kernel": bool(torch.equal(g_de, de_buf) and torch.equal(g_psd, psd_buf))}
         del g_clips, g_de, g_psd
 
+        # ---- next rows (8f ranks 2, 3): consumer-side input build on the 1 s features of every resident subject ----
+        # concept re-ordering + mean over the two windows + 310 columns + StandardScaler, one group per subject
+        from eeg2video_b200 import consumers
+        import numpy as np
+        f_de, _, _ = ops.de_psd_from_raw(raw, frontend.MODES["1s"])                 # (S*7*200, 2, 62, 5)
+        f_units = f_de.reshape(S * 1400, 2, 310)
+        perm_rng = np.random.default_rng(0)
+        gt = np.stack([perm_rng.permutation(40) + 1 for _ in range(7)])             # a synthetic label table
+        one = consumers.clip_index(range(6), gt, range(1, 41))                      # 1200 clips of a subject
+        idx = torch.from_numpy(np.concatenate([one + s_ * 1400 for s_ in range(S)]).astype(np.int32)).to(dev)
+
+        def c_step():
+            x = ops.select_units(f_units, idx, True).reshape(S, 1200, 310)
+            m, _, sc = ops.column_stats(x)
+            return ops.standardize(x, m, sc)
+        for _ in range(3):
+            c_step()
+        c_before = _lib.launch_count()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(args.steps):
+            c_out = c_step()
+        c1.record(stream)
+        torch.cuda.synchronize()
+        c_ms = c0.elapsed_time(c1) / args.steps
+        # bytes: gather reads 2 windows and writes x; the two statistics passes read x; the transform reads x, writes out
+        c_bytes = S * 1200 * 310 * 4 * (2 + 1 + 2 + 2)
+        next_rows["consumer_inputs_semantic_1s"] = {
+            "subjects": S, "rows": S * 1200, "cols": 310, "ms": c_ms, "us_per_subject": 1e3 * c_ms / S,
+            "launches_per_call": int((_lib.launch_count() - c_before) // args.steps),
+            "hbm_gbs": c_bytes / (c_ms * 1e-3) / 1e9, "hbm_frac": c_bytes / (c_ms * 1e-3) / 1e9 / measured_peaks()[0],
+            "note": "six small launches over 36 MB: launch-latency-bound, not a bandwidth claim",
+            "column_mean_abs_max": float(c_out.double().mean(dim=1).abs().max())}
+        del f_de, f_units, c_out
+
     # ---- end to end: pinned host recordings -> H2D -> fused kernel -> D2H of the features, every step ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     pipe = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode)

@@ -28,6 +28,10 @@ SIGNATURES = {
     "eegfe_de_psd_windows": (_int, [_ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr]),
     "eegfe_segment_clips": (_int, [_ptr, _int, _i64, _int, _i64, _i64, _i64, _int, _ptr, _ptr]),
     "eegfe_sliding_windows": (_int, [_ptr, _int, _i64, _int, _ptr, _ptr]),
+    "eegfe_select_units": (_int, [_ptr, _i64, _int, _int, _ptr, _i64, _int, _ptr, _ptr]),
+    "eegfe_column_stats_workspace": (_i64, [_i64, _i64, _int]),
+    "eegfe_column_stats": (_int, [_ptr, _i64, _i64, _int, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "eegfe_standardize": (_int, [_ptr, _i64, _i64, _int, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "eegfe_launch_geometry": (_int, [_int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
                                      ctypes.POINTER(_int)]),
     "eegfe_launch_count": (_i64, []),

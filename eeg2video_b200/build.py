@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libeegfe.so")
 SOURCES = ["eegfe_kernels.cu"]
-HEADERS = ["bandpower.cuh", "cplx.cuh", "eegfe_stream.cuh", "eegfe_tables.h", os.path.join("..", "..", "include", "eegfe.h")]
+HEADERS = ["bandpower.cuh", "cplx.cuh", "eegfe_stream.cuh", "eegfe_consumers.cuh", "eegfe_tables.h", os.path.join("..", "..", "include", "eegfe.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

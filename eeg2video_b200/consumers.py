@@ -1,0 +1,139 @@
+"""Consumer-side input build -- "next" rows beyond the core path.
+
+Everything that reads the reference's DE/PSD feature files starts with the same few steps; here they run on the
+features while they are still in HBM:
+
+* block selection + **concept re-ordering** by the label table: ``indices = [list(GT_label[i]).index(e) for e in
+  chosed_label]; eegdata[i][indices]`` (EEG2Video_New/Generation/models/train_semantic_predictor.py:87-91,
+  EEG2Video_New/Semantic/eeg_text.py:115-118);
+* **mean over the analysis windows** and flattening (channel, band) to 310 columns
+  (train_semantic_predictor.py:95, :114; EEG-VP/EEG_VP_train_test.py:232, :254-256);
+* **column standardisation** with ``sklearn.preprocessing.StandardScaler`` (train_semantic_predictor.py:47-48,
+  eeg_text.py:142-144, EEG_VP_train_test.py:259-267).
+
+The label table itself (``GT_label``, 7 x 40) is data of the SEED-DV protocol and is passed in by the caller.
+CUDA only, like the rest of the package: there is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def concept_order(gt_label_row, chosen_labels):
+    """Positions of `chosen_labels` inside one block's label row: ``[list(row).index(e) for e in chosen]``
+    (train_semantic_predictor.py:88).  Raises ValueError for a label that is not in the row, like list.index."""
+    row = [int(v) for v in np.asarray(gt_label_row).reshape(-1)]
+    return [row.index(int(e)) for e in chosen_labels]
+
+
+def clip_index(blocks, gt_label, chosen_labels, n_concepts=40, n_reps=5):
+    """int32 unit indices (into a (n_blocks * n_concepts * n_reps)-unit feature tensor) of the selected blocks'
+    clips, concepts in `chosen_labels` order, repetitions in recording order."""
+    gt_label = np.asarray(gt_label)
+    idx = []
+    for b in blocks:
+        order = concept_order(gt_label[b], chosen_labels) if gt_label is not None else list(range(n_concepts))
+        for c in order:
+            base = (int(b) * n_concepts + c) * n_reps
+            idx.extend(range(base, base + n_reps))
+    return np.asarray(idx, dtype=np.int32)
+
+
+def _as_units(features):
+    """(blocks, 40, 5, [W,] ch, 5) float32 CUDA -> contiguous (units, W, ch * 5) view + W."""
+    if features.dim() == 6:
+        b, c, r, w, ch, k = features.shape
+    elif features.dim() == 5:
+        b, c, r, ch, k = features.shape
+        w = 1
+    else:
+        raise ValueError("features must have shape (blocks, concepts, repetitions[, windows], channels, bands)")
+    if features.dtype != torch.float32:
+        features = features.to(torch.float32)
+    return features.contiguous().reshape(b * c * r, w, ch * k), (b, c, r, w, ch * k)
+
+
+def select_clips(features, blocks, gt_label=None, chosen_labels=None, mean_windows=False):
+    """Block selection + concept re-ordering (+ optional mean over the analysis windows) in one gather kernel.
+
+    Returns float32 (len(blocks) * len(chosen) * 5, [W,] ch * 5); with mean_windows the W axis is averaged away
+    (torch.mean(EEG, dim=1), train_semantic_predictor.py:114).
+    """
+    units, (b, c, r, w, cols) = _as_units(features)
+    chosen = list(range(1, c + 1)) if chosen_labels is None else list(chosen_labels)
+    if gt_label is None:
+        gt_label = np.tile(np.arange(1, c + 1), (b, 1))
+    idx = torch.from_numpy(clip_index(list(blocks), gt_label, chosen, c, r)).to(units.device)
+    out = ops.select_units(units, idx, bool(mean_windows))
+    if features.dim() == 5 and not mean_windows:
+        out = out.reshape(out.shape[0], cols)
+    return out
+
+
+class StandardScaler:
+    """sklearn.preprocessing.StandardScaler (with_mean=True, with_std=True) on CUDA tensors.
+
+    fit: per-column mean and population variance in float64, ``scale_ = sqrt(var_)`` with 1 for near-constant
+    columns; transform: ``float32((float64(x) - mean_) / scale_)`` (the reference's call sites all run in float64).  Attributes follow sklearn:
+    ``mean_``, ``var_``, ``scale_`` (float64 CUDA tensors), ``n_samples_seen_``, ``n_features_in_``.
+
+    Extension: a 3-D input (groups, samples, features) fits / transforms every group with its own statistics in
+    the same kernel launches (one group per subject or per split), statistics shaped (groups, features).
+    """
+
+    def fit(self, x):
+        x = self._check(x)
+        self.mean_, self.var_, self.scale_ = ops.column_stats(x)
+        self.n_samples_seen_ = int(x.shape[-2])
+        self.n_features_in_ = int(x.shape[-1])
+        self._groups = int(x.shape[0]) if x.dim() == 3 else None
+        return self
+
+    def transform(self, x):
+        if not hasattr(self, "scale_"):
+            raise RuntimeError("This StandardScaler instance is not fitted yet.")
+        x = self._check(x)
+        if x.shape[-1] != self.n_features_in_:
+            raise ValueError(f"X has {x.shape[-1]} features, but StandardScaler is expecting {self.n_features_in_} "
+                             "features as input.")
+        if (int(x.shape[0]) if x.dim() == 3 else None) != self._groups:
+            raise ValueError("X does not have the group axis the scaler was fitted with")
+        return ops.standardize(x, self.mean_, self.scale_)
+
+    def fit_transform(self, x):
+        return self.fit(x).transform(x)
+
+    @staticmethod
+    def _check(x):
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise RuntimeError("StandardScaler here is CUDA-only (no CPU fallback): pass a CUDA tensor")
+        if x.dim() not in (2, 3):
+            raise ValueError(f"Expected 2D array, got {x.dim()}D array instead")
+        if x.shape[-2] == 0:
+            raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by StandardScaler.")
+        x = x.to(torch.float32)
+        return x if x.stride(-1) == 1 else x.contiguous()
+
+
+def semantic_predictor_inputs(features, gt_label, chosen_labels, blocks=range(6)):
+    """The EEG side of the semantic-predictor dataset (train_semantic_predictor.py:86-95, :114, :47-48 for the 1 s
+    features; eeg_text.py:115-125, :142-144 for the 2 s ones): selected blocks, concepts in label order, mean over
+    the windows, 310 columns, standardised.  Returns (x, scaler)."""
+    x = select_clips(features, blocks, gt_label, chosen_labels, mean_windows=True)
+    scaler = StandardScaler().fit(x)
+    return scaler.transform(x), scaler
+
+
+def classifier_fold_inputs(features, test_block):
+    """Leave-one-block-out split of EEG-VP/EEG_VP_train_test.py:232-267: every (concept, repetition, window) of a
+    block is one sample of 310 columns; train = the other blocks in block order, validation = the block before the
+    test block; each split is standardised with its OWN statistics (as the reference does).
+    Returns {"train": x, "test": x, "val": x} float32 CUDA tensors."""
+    units, (b, c, r, w, cols) = _as_units(features)
+    per_block = units.reshape(b, c * r * w, cols)
+    val_block = test_block - 1 if test_block > 0 else b - 1
+    train = torch.cat([per_block[i] for i in range(b) if i != test_block])
+    return {"train": StandardScaler().fit_transform(train),
+            "test": StandardScaler().fit_transform(per_block[test_block]),
+            "val": StandardScaler().fit_transform(per_block[val_block])}

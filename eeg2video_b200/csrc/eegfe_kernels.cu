@@ -754,6 +754,8 @@ static Job raw_geometry(int n_ch, int64_t block_stride, int64_t ch_stride, int f
 
 }  // namespace eegfe
 
+#include "eegfe_consumers.cuh"
+
 using namespace eegfe;
 
 extern "C" {
@@ -980,6 +982,74 @@ int eegfe_sliding_windows(const void* clips, int dtype, int64_t n_clips, int n_c
   if (es >= 4 && base_ok) sliding_windows_kernel<8><<<grid, threads, 0, s>>>(src, dst, n_clips, n_ch, es);
   else if (es >= 4 || base_ok) sliding_windows_kernel<4><<<grid, threads, 0, s>>>(src, dst, n_clips, n_ch, es);
   else sliding_windows_kernel<2><<<grid, threads, 0, s>>>(src, dst, n_clips, n_ch, es);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+int eegfe_select_units(const float* feat, int64_t n_units_in, int n_windows, int n_cols, const int* src_index,
+                       int64_t n_out, int reduce_windows, float* out, void* stream)
+{
+  if (n_units_in < 0 || n_out < 0 || n_windows <= 0 || n_cols <= 0) return EEGFE_EINVAL;
+  if (n_out == 0) return 0;
+  if (feat == nullptr || src_index == nullptr || out == nullptr) return EEGFE_EINVAL;
+  const long long total = n_out * (reduce_windows ? n_cols : static_cast<long long>(n_windows) * n_cols);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  select_units_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      feat, src_index, n_out, n_windows, n_cols, reduce_windows ? 1 : 0, out);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+int64_t eegfe_column_stats_workspace(int64_t n_groups, int64_t n_rows, int n_cols)
+{
+  if (n_groups < 0 || n_rows < 0 || n_cols <= 0) return EEGFE_EINVAL;
+  const int64_t chunks = (n_rows + kStatRowsPerBlock - 1) / kStatRowsPerBlock;
+  return 2 * (n_groups > 0 ? n_groups : 1) * (chunks > 0 ? chunks : 1) * n_cols;
+}
+
+int eegfe_column_stats(const float* x, int64_t n_groups, int64_t n_rows, int n_cols, int64_t row_stride,
+                       int64_t group_stride, double* workspace, double* mean, double* var, double* scale, void* stream)
+{
+  if (n_groups < 0 || n_rows < 0 || n_cols <= 0 || row_stride < n_cols || group_stride < 0) return EEGFE_EINVAL;
+  if (n_groups == 0) return 0;
+  if (workspace == nullptr || mean == nullptr || var == nullptr || scale == nullptr) return EEGFE_EINVAL;
+  if (n_rows > 0 && x == nullptr) return EEGFE_EINVAL;
+  const int64_t chunks64 = (n_rows + kStatRowsPerBlock - 1) / kStatRowsPerBlock;
+  if (chunks64 > 0x7fffffff || n_groups > 65535) return EEGFE_EINVAL;
+  const int chunks = static_cast<int>(chunks64);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const dim3 part(static_cast<unsigned>(chunks), static_cast<unsigned>(n_groups));
+  const dim3 fin(static_cast<unsigned>((n_cols + 127) / 128), static_cast<unsigned>(n_groups));
+  if (chunks > 0) {
+    column_partial_kernel<0><<<part, 256, 0, s>>>(x, n_rows, n_cols, row_stride, group_stride, nullptr, workspace);
+    ++g_launches;
+  }
+  column_finish_kernel<0><<<fin, 128, 0, s>>>(workspace, chunks, n_rows, n_cols, nullptr, mean, nullptr);
+  ++g_launches;
+  if (chunks > 0) {
+    column_partial_kernel<1><<<part, 256, 0, s>>>(x, n_rows, n_cols, row_stride, group_stride, mean, workspace);
+    ++g_launches;
+  }
+  column_finish_kernel<1><<<fin, 128, 0, s>>>(workspace, chunks, n_rows, n_cols, mean, var, scale);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+int eegfe_standardize(const float* x, int64_t n_groups, int64_t n_rows, int n_cols, int64_t row_stride,
+                      int64_t group_stride, const double* mean, const double* scale, float* out, void* stream)
+{
+  if (n_groups < 0 || n_rows < 0 || n_cols <= 0 || row_stride < n_cols || group_stride < 0) return EEGFE_EINVAL;
+  if (n_rows == 0 || n_groups == 0) return 0;
+  if (x == nullptr || mean == nullptr || scale == nullptr || out == nullptr || n_groups > 65535) return EEGFE_EINVAL;
+  const long long total = n_rows * n_cols;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  const dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(n_groups));
+  standardize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n_rows, n_cols, row_stride, group_stride,
+                                                                          mean, scale, out);
   ++g_launches;
   return static_cast<int>(cudaGetLastError());
 }

@@ -231,3 +231,93 @@ def channel_stats(raw: torch.Tensor, block_mask: torch.Tensor) -> Tuple[torch.Te
 def _(raw, block_mask):
     mean = raw.new_empty((raw.shape[1],), dtype=torch.float64)
     return mean, torch.empty_like(mean)
+
+
+@torch.library.custom_op("eeg2video::select_units", mutates_args=(), device_types="cuda")
+def select_units(feat: torch.Tensor, src_index: torch.Tensor, reduce_windows: bool) -> torch.Tensor:
+    """feat float32 (n_units, W, cols), src_index int32 (n_out,) -> (n_out, W, cols), or (n_out, cols) = mean over
+    the W windows when `reduce_windows`."""
+    _require_cuda(feat, "feat")
+    if feat.dim() != 3 or feat.dtype != torch.float32 or not feat.is_contiguous():
+        raise ValueError("feat must be contiguous float32 (n_units, n_windows, n_cols)")
+    if src_index.dtype != torch.int32 or src_index.dim() != 1 or src_index.device != feat.device:
+        raise ValueError("src_index must be an int32 vector on the same device")
+    n_units, n_win, cols = feat.shape
+    n_out = src_index.shape[0]
+    shape = (n_out, cols) if reduce_windows else (n_out, n_win, cols)
+    with torch.cuda.device(feat.device):
+        out = torch.empty(shape, dtype=torch.float32, device=feat.device)
+        _lib.check(_lib.load().eegfe_select_units(feat.data_ptr(), n_units, n_win, cols,
+                                                  src_index.contiguous().data_ptr(), n_out, int(bool(reduce_windows)),
+                                                  out.data_ptr(), _stream(feat)))
+    return out
+
+
+@select_units.register_fake
+def _(feat, src_index, reduce_windows):
+    if reduce_windows:
+        return feat.new_empty((src_index.shape[0], feat.shape[2]))
+    return feat.new_empty((src_index.shape[0], feat.shape[1], feat.shape[2]))
+
+
+def _as_groups(x, name):
+    """(n_rows, n_cols) or (n_groups, n_rows, n_cols) float32 with unit column stride -> (x3d, squeeze)."""
+    _require_cuda(x, name)
+    if x.dim() not in (2, 3) or x.dtype != torch.float32 or (x.numel() > 0 and x.stride(-1) != 1):
+        raise ValueError(f"{name} must be float32 ([n_groups,] n_rows, n_cols) with contiguous columns")
+    return (x.unsqueeze(0), True) if x.dim() == 2 else (x, False)
+
+
+def _strides(x3):
+    g, n, c = x3.shape
+    return (x3.stride(1) if n > 1 else c), (x3.stride(0) if g > 1 else 0)
+
+
+@torch.library.custom_op("eeg2video::column_stats", mutates_args=(), device_types="cuda")
+def column_stats(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x float32 ([G,] n_rows, n_cols) -> (mean, var, scale) float64 ([G,] n_cols), StandardScaler rules; with a
+    leading group axis every group gets its own statistics in the same launches."""
+    x3, squeeze = _as_groups(x, "x")
+    g, n_rows, n_cols = x3.shape
+    row_stride, group_stride = _strides(x3)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        work = torch.empty(int(lib.eegfe_column_stats_workspace(g, n_rows, n_cols)), dtype=torch.float64,
+                           device=x.device)
+        mean = torch.empty((g, n_cols), dtype=torch.float64, device=x.device)
+        var = torch.empty_like(mean)
+        scale = torch.empty_like(mean)
+        _lib.check(lib.eegfe_column_stats(x3.data_ptr(), g, n_rows, n_cols, row_stride, group_stride,
+                                          work.data_ptr(), mean.data_ptr(), var.data_ptr(), scale.data_ptr(),
+                                          _stream(x)))
+    if squeeze:
+        return mean[0], var[0], scale[0]
+    return mean, var, scale
+
+
+@column_stats.register_fake
+def _(x):
+    m = x.new_empty(tuple(x.shape[:-2]) + (x.shape[-1],), dtype=torch.float64)
+    return m, torch.empty_like(m), torch.empty_like(m)
+
+
+@torch.library.custom_op("eeg2video::standardize", mutates_args=(), device_types="cuda")
+def standardize(x: torch.Tensor, mean: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """float32((double(x) - mean) / scale), float32 ([G,] n_rows, n_cols) -> float32 contiguous."""
+    x3, squeeze = _as_groups(x, "x")
+    g, n_rows, n_cols = x3.shape
+    want = (n_cols,) if squeeze else (g, n_cols)
+    for name, v in (("mean", mean), ("scale", scale)):
+        if v.dtype != torch.float64 or tuple(v.shape) != want or not v.is_contiguous() or v.device != x.device:
+            raise ValueError(f"{name} must be a contiguous float64 {want} tensor on {x.device}")
+    row_stride, group_stride = _strides(x3)
+    with torch.cuda.device(x.device):
+        out = torch.empty((g, n_rows, n_cols), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().eegfe_standardize(x3.data_ptr(), g, n_rows, n_cols, row_stride, group_stride,
+                                                 mean.data_ptr(), scale.data_ptr(), out.data_ptr(), _stream(x)))
+    return out[0] if squeeze else out
+
+
+@standardize.register_fake
+def _(x, mean, scale):
+    return x.new_empty(x.shape)

@@ -154,6 +154,38 @@ int eegfe_segment_clips(const void* raw, int dtype, int64_t n_blocks, int n_ch, 
  */
 int eegfe_sliding_windows(const void* clips, int dtype, int64_t n_clips, int n_ch, void* windows, void* stream);
 
+/*
+ * NEXT ROWS: the first thing every consumer of the feature files does.
+ *
+ * eegfe_select_units -- pick and re-order clips ("units" of [n_windows][n_cols] floats, n_cols = n_ch * 5), optionally
+ * averaging the analysis windows.  Replaces the block selection + GT_label concept re-ordering + window mean of
+ * train_semantic_predictor.py:87-95, :114 and eeg_text.py:115-125 (host computes src_index from the label table):
+ *   reduce_windows == 0 : out[j][w][i] = feat[src_index[j]][w][i]                 out: [n_out][n_windows][n_cols]
+ *   reduce_windows != 0 : out[j][i]    = mean_w feat[src_index[j]][w][i]          out: [n_out][n_cols]
+ * src_index: device int32 [n_out], each in [0, n_units_in).
+ */
+int eegfe_select_units(const float* feat, int64_t n_units_in, int n_windows, int n_cols, const int* src_index,
+                       int64_t n_out, int reduce_windows, float* out, void* stream);
+
+/*
+ * Column statistics and standardisation with sklearn.preprocessing.StandardScaler semantics (the reference's
+ * `StandardScaler().fit(x); transform(x)` at EEG_VP_train_test.py:259-267, train_semantic_predictor.py:47-48,
+ * eeg_text.py:142-144): mean and population variance per column in float64 (corrected two-pass algorithm, fixed
+ * summation order), scale = sqrt(var) with 1 for near-constant columns (sklearn's _is_constant_feature bound);
+ * transform = float32((double(x) - mean) / scale): the reference's call sites all run the scaler in float64 (float64
+ * arrays, or torch tensors that scikit-learn converts to float64), so this is its result rounded once.  The third-party arithmetic is scikit-learn's (not pinned by the reference's requirements.txt;
+ * restated from scikit-learn 1.9.0 as installed in the build container: preprocessing/_data.py, utils/extmath.py).
+ * x: float32 [n_groups][n_rows][n_cols] with strides (group_stride, row_stride, 1) in elements; every group is an
+ * independent matrix with its own statistics (one subject, one split).  mean, var, scale: device double
+ * [n_groups][n_cols].  out: float32 [n_groups][n_rows][n_cols], contiguous.
+ * workspace: device double [eegfe_column_stats_workspace(n_groups, n_rows, n_cols)].
+ */
+int64_t eegfe_column_stats_workspace(int64_t n_groups, int64_t n_rows, int n_cols);
+int eegfe_column_stats(const float* x, int64_t n_groups, int64_t n_rows, int n_cols, int64_t row_stride,
+                       int64_t group_stride, double* workspace, double* mean, double* var, double* scale, void* stream);
+int eegfe_standardize(const float* x, int64_t n_groups, int64_t n_rows, int n_cols, int64_t row_stride,
+                      int64_t group_stride, const double* mean, const double* scale, float* out, void* stream);
+
 /* Introspection used by bench.py / tests: kernel launch geometry chosen for `mode` on the current device. */
 int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int* rows_per_tile);
 
