@@ -451,6 +451,7 @@ def run_gpu_arm(args):
 
     # ---- end to end: pinned host recordings -> H2D -> fused kernel -> D2H of the features, every step ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    numa_cpus = pipeline.bind_to_gpu_numa_node(dev) if world > 1 else None     # node-local pinned buffers per rank
     pipe = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode)
     raw_host = torch.empty((S * 7, 62, 104000), dtype=torch.float32).pin_memory()
     raw_host.copy_(raw)
@@ -534,6 +535,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes(S * 7)),
                     "d2h_bytes_per_step": int(2 * de_host.numel() * 4), "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_result": e2e_ok,
+                    "rank0_numa_cpus": None if numa_cpus is None else len(numa_cpus),
                     "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
                             "D2H of DE+PSD, 3 streams) -> pinned host features"},
             "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),

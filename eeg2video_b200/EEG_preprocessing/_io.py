@@ -47,3 +47,29 @@ def finish(tensors, like_torch, dtype):
         tdtype = torch.float64 if dtype == np.float64 else torch.float32
         return tuple(t.to(tdtype) for t in tensors)
     return tuple(t.cpu().numpy().astype(dtype, copy=False) for t in tensors)
+
+
+def convert_directory(in_dir, out_dirs, convert, names=None, accept=None, log=print):
+    """The file loop every reference script repeats: for each ``sub{N}.npy`` in ``in_dir`` (or the explicit
+    ``names``), load it, run ``convert`` and save result k under ``out_dirs[k]`` with the same file name.
+    ``accept(array)`` may veto a file (returns a reason string).  Returns the names written."""
+    import os
+    for d in out_dirs:
+        os.makedirs(d, exist_ok=True)
+    if names is None:
+        names = sorted(n for n in os.listdir(in_dir) if n.endswith(".npy"))
+    written = []
+    for name in names:
+        array = np.load(os.path.join(in_dir, name))
+        reason = accept(array) if accept is not None else None
+        if reason:
+            log(f"Skipping {name}: {reason}")
+            continue
+        results = convert(array)
+        if not isinstance(results, tuple):
+            results = (results,)
+        for d, result in zip(out_dirs, results):
+            np.save(os.path.join(d, name), result)
+        log(f"{name}: " + ", ".join(f"{os.path.join(d, name)} {tuple(r.shape)}" for d, r in zip(out_dirs, results)))
+        written.append(name)
+    return written

@@ -15,14 +15,6 @@ from . import _io
 fre = 200
 
 
-def get_files_names_in_directory(directory):
-    files_names = []
-    for root, _, filenames in os.walk(directory):
-        for filename in filenames:
-            files_names.append(filename)
-    return files_names
-
-
 def extract_de_psd_1s(raw, fs=200):
     """(B, C, R, ch, 400) -> (DE, PSD), each (B, C, R, 2, ch, 5) float64; window k = samples [200k, 200k+200)
     (reference :34-35, :46-53)."""
@@ -36,14 +28,9 @@ def extract_de_psd_1s(raw, fs=200):
 
 def main(in_dir="./data/Preprocessing/Segmented_Rawf_200Hz_2s/",
          de_dir="./data/Preprocessing/DE_1per1s", psd_dir="./data/Preprocessing/PSD_1per1s"):
-    for subname in get_files_names_in_directory(in_dir):
-        loaded_data = np.load(os.path.join(in_dir, subname))
-        print("Successfully loaded .npy file.")
-        DE_data, PSD_data = extract_de_psd_1s(loaded_data, fre)
-        os.makedirs(de_dir, exist_ok=True)
-        os.makedirs(psd_dir, exist_ok=True)
-        np.save(os.path.join(de_dir, subname), DE_data)
-        np.save(os.path.join(psd_dir, subname), PSD_data)
+    """Script behaviour of the reference (:17-24, :56-58): every file found under ``in_dir``."""
+    names = sorted(f for _, _, files in os.walk(in_dir) for f in files)
+    return _io.convert_directory(in_dir, (de_dir, psd_dir), lambda clips: extract_de_psd_1s(clips, fre), names=names)
 
 
 if __name__ == "__main__":

@@ -3,8 +3,6 @@
 Input (7, 40, 5, 62, 400); output DE and PSD (7, 40, 5, 62, 5) float32.  One kernel launch per subject instead of
 1400 DE_PSD calls.
 """
-import os
-
 import numpy as np
 
 from .. import frontend
@@ -26,15 +24,12 @@ def extract_de_psd_raw(raw, fs=200):
     return _io.finish((de, psd), like_torch, np.float32)
 
 
-if __name__ == "__main__":
-    for subname in range(1, 21):
-        loaded_data = np.load('./data/Preprocessing/Segmented_Rawf_200Hz_2s/sub' + str(subname) + '.npy')
-        print("Successfully loaded .npy file.")
-        DE_data, PSD_data = extract_de_psd_raw(loaded_data, fre)
+def main(in_dir="./data/Preprocessing/Segmented_Rawf_200Hz_2s", de_dir="./data/Preprocessing/DE_1per2s",
+         psd_dir="./data/Preprocessing/PSD_1per2s", subjects=range(1, 21)):
+    """Script behaviour of the reference (:30-42): subjects 1..20, DE_1per2s/ and PSD_1per2s/ next to the input."""
+    return _io.convert_directory(in_dir, (de_dir, psd_dir), lambda clips: extract_de_psd_raw(clips, fre),
+                                 names=[f"sub{n}.npy" for n in subjects])
 
-        os.makedirs("./data/Preprocessing/DE_1per2s", exist_ok=True)
-        os.makedirs("./data/Preprocessing/PSD_1per2s", exist_ok=True)
-        np.save("./data/Preprocessing/DE_1per2s/sub" + str(subname) + ".npy", DE_data)
-        np.save("./data/Preprocessing/PSD_1per2s/sub" + str(subname) + ".npy", PSD_data)
-        print(f"Saved DE data in ./data/Preprocessing/DE_1per2s/sub{str(subname)}.npy")
-        print(f"Saved PSD data in ./data/Preprocessing/PSD_1per2s/sub{str(subname)}.npy")
+
+if __name__ == "__main__":
+    main()

@@ -2,7 +2,6 @@
 /root/reference/EEG_preprocessing/extract_DE_PSD_features_1per500ms.py (same CLI flags and defaults).
 """
 import argparse
-import os
 
 import numpy as np
 
@@ -47,28 +46,17 @@ def extract_de_psd_sw(raw, fs, win_sec):
     return _io.finish((de, psd), like_torch, np.float32)
 
 
+def main(argv=None):
+    """CLI of the reference script (:32-58): --raw_dir --de_dir --psd_dir --subs, same defaults."""
+    cli = argparse.ArgumentParser(description=__doc__)
+    cli.add_argument("--raw_dir", default="./data/Preprocessing/Segmented_500ms_sw")
+    cli.add_argument("--de_dir", default="./data/Preprocessing/DE_500ms_sw")
+    cli.add_argument("--psd_dir", default="./data/Preprocessing/PSD_500ms_sw")
+    cli.add_argument("--subs", nargs="+", type=int, default=list(range(1, 21)))
+    opt = cli.parse_args(argv)
+    return _io.convert_directory(opt.raw_dir, (opt.de_dir, opt.psd_dir), lambda windows: extract_de_psd_sw(windows, 200, 0.5),
+                                 names=[f"sub{n}.npy" for n in opt.subs])
+
+
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--raw_dir', default="./data/Preprocessing/Segmented_500ms_sw", help='windowed raw EEG .npy folder')
-    parser.add_argument('--de_dir', default="./data/Preprocessing/DE_500ms_sw", help='where DE is saved')
-    parser.add_argument('--psd_dir', default="./data/Preprocessing/PSD_500ms_sw", help='where PSD is saved')
-    parser.add_argument('--subs', nargs='+', type=int, default=list(range(1, 21)), help='subject numbers')
-    args = parser.parse_args()
-
-    FS = 200
-    WIN_SEC = 0.5
-
-    os.makedirs(args.de_dir, exist_ok=True)
-    os.makedirs(args.psd_dir, exist_ok=True)
-
-    for sub in args.subs:
-        raw_path = os.path.join(args.raw_dir, f'sub{sub}.npy')
-        de_out_path = os.path.join(args.de_dir, f'sub{sub}.npy')
-        psd_out_path = os.path.join(args.psd_dir, f'sub{sub}.npy')
-        print(f"Processing subject {sub}...")
-
-        raw = np.load(raw_path)
-        DE_data, PSD_data = extract_de_psd_sw(raw, FS, WIN_SEC)
-        np.save(de_out_path, DE_data)
-        np.save(psd_out_path, PSD_data)
-        print(f"Saved DE/PSD: {os.path.basename(de_out_path)} / {os.path.basename(psd_out_path)}")
+    main()

@@ -16,48 +16,42 @@ from . import _io
 __all__ = ["extract_2s_segment", "segment_all_files"]
 
 FS = 200
-_BASELINE_SEC = 3
-_REPS_PER_CONCEPT = 5
-_CONCEPTS_PER_BLOCK = 40
+HINT_SECONDS, CLIP_SECONDS = 3, 2           # a concept = 3 s hint + 5 clips of 2 s (SEED-DV protocol)
+N_BLOCKS, N_CONCEPTS, N_REPS = 7, 40, 5
+_INDEX_LIMITS = (("block", N_BLOCKS), ("concept", N_CONCEPTS), ("repetition", N_REPS))
 
 
-def extract_2s_segment(
-    *,
-    block,
-    concept,
-    repetition,
-    subject=None,
-    eeg_root="./data/EEG",
-    fs=FS,
-    data=None,
-):
-    """Return one raw 2-second EEG segment (62 x 2*fs) as a view of ``data[block]``.
+def clip_start(concept, repetition, fs=FS):
+    """First sample of clip (concept, repetition) inside a block row: c * 13 fs + 3 fs + r * 2 fs."""
+    per_concept = (HINT_SECONDS + N_REPS * CLIP_SECONDS) * fs
+    return concept * per_concept + HINT_SECONDS * fs + repetition * CLIP_SECONDS * fs
 
-    block, concept, repetition : indices of the segment inside a recording.
-    subject : 1-indexed subject id, required when ``data`` is None (``eeg_root/sub{subject}.npy`` is memory-mapped).
-    data : pre-loaded recording of shape (7, 62, T), numpy or torch.
+
+def _open_recording(subject, eeg_root):
+    if subject is None or subject < 1:
+        raise ValueError("`subject` must be >= 1 when no `data` is provided")
+    path = os.path.join(eeg_root, f"sub{subject}.npy")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    return np.load(path, mmap_mode="r")
+
+
+def extract_2s_segment(*, block, concept, repetition, subject=None, eeg_root="./data/EEG", fs=FS, data=None):
+    """One raw 2-second EEG segment, shape (channels, 2*fs), as a VIEW of ``data[block]`` -- same keyword-only
+    contract, defaults and exceptions as the reference function (segment_raw_signals_200Hz.py:15-70).
+
+    ``data``: recording (7, channels, T), numpy (memory maps included) or torch; when omitted,
+    ``eeg_root/sub{subject}.npy`` is memory-mapped (subject ids start at 1).
     """
-    if data is None:
-        if subject is None or subject < 1:
-            raise ValueError("`subject` must be >= 1 when no `data` is provided")
-        path = os.path.join(eeg_root, f"sub{subject}.npy")
-        if not os.path.exists(path):
-            raise FileNotFoundError(path)
-        data = np.load(path, mmap_mode="r")
-
-    if not 0 <= block <= 6:
-        raise ValueError("`block` must be in [0, 6]")
-    if not 0 <= concept < _CONCEPTS_PER_BLOCK:
-        raise ValueError("`concept` must be in [0, 39]")
-    if not 0 <= repetition < _REPS_PER_CONCEPT:
-        raise ValueError("`repetition` must be in [0, 4]")
-
-    clip_len = 2 * fs
-    first = concept * (_BASELINE_SEC * fs + _REPS_PER_CONCEPT * clip_len) + _BASELINE_SEC * fs + repetition * clip_len
-    segment = data[block][:, first:first + clip_len]
-    if segment.shape[1] != clip_len:
+    recording = data if data is not None else _open_recording(subject, eeg_root)
+    for (name, count), value in zip(_INDEX_LIMITS, (block, concept, repetition)):
+        if not 0 <= value < count:
+            raise ValueError(f"`{name}` must be in [0, {count - 1}]")
+    lo = clip_start(concept, repetition, fs)
+    view = recording[block][:, lo:lo + CLIP_SECONDS * fs]
+    if view.shape[1] != CLIP_SECONDS * fs:
         raise RuntimeError("Segment length mismatch")
-    return segment
+    return view
 
 
 def segment_subject(data, fs=FS):
@@ -66,7 +60,7 @@ def segment_subject(data, fs=FS):
     numpy in -> numpy out, torch CUDA in -> torch CUDA out.  Bit-exact with 1400 calls of extract_2s_segment.
     """
     like_torch = _io.is_torch(data)
-    if data.shape[-1] < _CONCEPTS_PER_BLOCK * (_BASELINE_SEC + 2 * _REPS_PER_CONCEPT) * fs:
+    if data.shape[-1] < clip_start(N_CONCEPTS, 0, fs) - HINT_SECONDS * fs:
         raise RuntimeError("Segment length mismatch")
     if like_torch:
         dev = data if data.is_cuda else data.to(_io.device())
@@ -79,19 +73,17 @@ def segment_subject(data, fs=FS):
     return clips if like_torch else clips.cpu().numpy()
 
 
-def segment_all_files(
-    eeg_root="./data/EEG",
-    output_dir="./data/Preprocessing/Segmented_Rawf_200Hz_2s",
-    fs=FS,
-):
-    """Segment all EEG files into ``(7, 40, 5, 62, 2*fs)`` arrays (one ``sub{N}.npy`` per input file)."""
+def segment_all_files(eeg_root="./data/EEG", output_dir="./data/Preprocessing/Segmented_Rawf_200Hz_2s", fs=FS):
+    """Write one ``(7, 40, 5, channels, 2*fs)`` clip array per ``sub{N}.npy`` recording found in ``eeg_root``
+    (reference: segment_raw_signals_200Hz.py:73-110; same defaults, same file naming)."""
     os.makedirs(output_dir, exist_ok=True)
-
-    sub_list = [f for f in os.listdir(eeg_root) if f.endswith(".npy")]
-    for subname in sub_list:
-        int(os.path.splitext(subname)[0].replace("sub", ""))     # same file-name contract as the reference (:83)
-        data = np.load(os.path.join(eeg_root, subname))
-        np.save(os.path.join(output_dir, subname), segment_subject(data[:7], fs))
+    for name in sorted(os.listdir(eeg_root)):
+        stem, ext = os.path.splitext(name)
+        if ext != ".npy":
+            continue
+        int(stem.replace("sub", ""))                 # the reference's file-name contract: sub{N}.npy, else ValueError
+        recording = np.load(os.path.join(eeg_root, name))
+        np.save(os.path.join(output_dir, name), segment_subject(recording[:N_BLOCKS], fs))
 
 
 if __name__ == "__main__":

@@ -3,8 +3,6 @@
 The function returns a strided, read-only VIEW exactly like the reference (:11-19); nothing is copied.  The
 script entry point materialises the windows with the device gather kernel (bit-exact) before saving.
 """
-import os
-
 import numpy as np
 import torch
 from numpy.lib.stride_tricks import as_strided
@@ -41,22 +39,16 @@ def materialize_windows(data):
     return out if like_torch else out.cpu().numpy()
 
 
+def main(in_dir="./data/Preprocessing/Segmented_Rawf_200Hz_2s", fs=200, win_s=0.5, step_s=0.25):
+    """Script behaviour of the reference (:24-57): 500 ms windows every 250 ms -> Segmented_500ms_sw/."""
+    if (int(fs * win_s), int(fs * step_s)) != (100, 50):
+        raise NotImplementedError("the materialising kernel is built for 100-sample windows every 50 samples")
+    out_dir = f"./data/Preprocessing/Segmented_{int(1000 * win_s)}ms_sw"
+
+    def wrong_shape(clips):
+        return None if clips.ndim == 5 and clips.shape[-1] == 2 * fs else f"unexpected shape {clips.shape}"
+    return _io.convert_directory(in_dir, (out_dir,), materialize_windows, accept=wrong_shape)
+
+
 if __name__ == "__main__":
-
-    INPUT_DIR = './data/Preprocessing/Segmented_Rawf_200Hz_2s'
-    FS = 200
-    WIN_S = 0.5
-    STEP_S = 0.25
-    OUTPUT_DIR = f'./data/Preprocessing/Segmented_{int(1000*WIN_S)}ms_sw'
-    os.makedirs(OUTPUT_DIR, exist_ok=True)
-
-    for fname in os.listdir(INPUT_DIR):
-        if not fname.endswith('.npy'):
-            continue
-        data = np.load(os.path.join(INPUT_DIR, fname))
-        if data.ndim != 5 or data.shape[-1] != 2 * FS:
-            print(f"Skipping {fname}: unexpected shape {data.shape}")
-            continue
-        windows = materialize_windows(data)
-        np.save(os.path.join(OUTPUT_DIR, fname), windows)
-        print(f"Saved segmented windows for {fname} -> {windows.shape}")
+    main()

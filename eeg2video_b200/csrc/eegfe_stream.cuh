@@ -29,6 +29,9 @@
 
 namespace eegfe {
 
+#ifndef EEGFE_STREAM_WARPS
+#define EEGFE_STREAM_WARPS 16
+#endif
 struct StreamCfg {
   static constexpr int kRows = 16;            // rows per tile
   static constexpr int kWindows = 7;
@@ -37,7 +40,7 @@ struct StreamCfg {
   static constexpr int kRowStride = 404;      // floats; bank skew, see Cfg
   static constexpr int kRowBytes = kLoad * 4;
   static constexpr int kSlots = 7;
-  static constexpr int kWarps = 16;
+  static constexpr int kWarps = EEGFE_STREAM_WARPS;
   static constexpr int kThreads = kWarps * 32;
   static constexpr int kUnits = kRows * kWindows;          // 112
   static constexpr int kHalfPasses = kUnits / 16;          // 7

@@ -16,6 +16,34 @@ from . import _lib, frontend, ops
 CONCEPTS, HINT, CLIPS_LEN, CONCEPT_LEN = 40, 600, 2000, 2600
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (Linux sysfs), so that the pinned host
+    buffers it allocates next are node-local to the GPU's PCIe root.  Returns the CPU set used, or None when the
+    platform does not say (VMs often report numa_node = -1) -- in which case nothing is changed."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(torch.device(device)).pci_bus_id
+        dom = torch.cuda.get_device_properties(torch.device(device)).pci_domain_id
+        dev = torch.cuda.get_device_properties(torch.device(device)).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        with open(os.path.join(path, "numa_node")) as f:
+            if int(f.read().strip()) < 0:
+                return None
+        with open(os.path.join(path, "local_cpulist")) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 class HostPipeline:
     """Reusable staging buffers + streams for `features_from_host`.
 

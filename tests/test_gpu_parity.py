@@ -373,3 +373,35 @@ def test_glmnet_inputs_need_aligned_rows():
     raw = synth.synth_blocks(1, 3, device=DEV, channels=4, block_len=104001)
     with pytest.raises(RuntimeError, match="invalid argument"):
         glmnet_inputs.build_inputs(raw, torch.zeros(4), torch.ones(4))
+
+
+# ---- script entry points (A8): directory conventions and CLI flags of the reference ------------------------------------
+def test_script_entry_points_follow_the_reference_layout(tmp_path, monkeypatch):
+    """segment_all_files -> sliding-window script -> the three feature scripts, all on ./data/... defaults."""
+    from eeg2video_b200.EEG_preprocessing import extract_DE_PSD_features_1per1s as s1
+    from eeg2video_b200.EEG_preprocessing import extract_DE_PSD_features_1per2s as s2
+    from eeg2video_b200.EEG_preprocessing import extract_DE_PSD_features_1per500ms as s5
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(17)
+    (tmp_path / "data" / "EEG").mkdir(parents=True)
+    for sub in (1, 2):
+        np.save(tmp_path / "data" / "EEG" / f"sub{sub}.npy", (30 * rng.standard_normal((7, 3, 104000))).astype(np.float32))
+    seg.segment_all_files()                                                       # ./data/EEG -> Segmented_Rawf_200Hz_2s
+    pre = tmp_path / "data" / "Preprocessing"
+    clips = np.load(pre / "Segmented_Rawf_200Hz_2s" / "sub2.npy")
+    assert clips.shape == (7, 40, 5, 3, 400) and clips.dtype == np.float32
+    assert ssw.main() == ["sub1.npy", "sub2.npy"]                                 # -> Segmented_500ms_sw
+    wins = np.load(pre / "Segmented_500ms_sw" / "sub2.npy")
+    assert wins.shape == (7, 40, 5, 7, 3, 100) and np.array_equal(wins, oracle.seg_sliding_window(clips, 0.5, 0.25))
+    assert s5.main(["--subs", "2"]) == ["sub2.npy"]                               # CLI flags of the reference
+    assert s2.main(subjects=(1, 2)) == ["sub1.npy", "sub2.npy"]
+    assert s1.main() == ["sub1.npy", "sub2.npy"]
+    de5 = np.load(pre / "DE_500ms_sw" / "sub2.npy")
+    de2 = np.load(pre / "DE_1per2s" / "sub2.npy")
+    psd1 = np.load(pre / "PSD_1per1s" / "sub2.npy")
+    assert de5.shape == (7, 40, 5, 7, 3, 5) and de5.dtype == np.float32
+    assert de2.shape == (7, 40, 5, 3, 5) and de2.dtype == np.float32
+    assert psd1.shape == (7, 40, 5, 2, 3, 5) and psd1.dtype == np.float64
+    assert not (pre / "DE_500ms_sw" / "sub1.npy").exists()                        # --subs 2 only
+    de_ref, _ = oracle.de_psd_closed_form(wins[0, 0], 200, 0.5)
+    assert np.max(np.abs(de5[0, 0] - de_ref)) <= 1e-4
