@@ -350,6 +350,29 @@ def run_gpu_arm(args):
         elapsed_ms = float(t.item())
     value = world * cw_step_gpu * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- BASELINE configs[1] as written: ONE subject, one launch (latency-bound; SURVEY.md 8d asks for us per call) ----
+    single = None
+    if rank == 0:
+        one = raw[:7]
+        s_de = torch.empty((7 * 200, ops.WINDOWS_PER_CLIP[mode_id], 62, 5), dtype=torch.float32, device=dev)
+        s_psd = torch.empty_like(s_de)
+
+        def s_step():
+            _lib.check(lib.eegfe_de_psd_from_raw(one.data_ptr(), 7, 62, 104000, one.stride(0), one.stride(1), mode_id,
+                                                 s_de.data_ptr(), s_psd.data_ptr(), status.data_ptr(),
+                                                 stream.cuda_stream))
+        for _ in range(3):
+            s_step()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(50):
+            s_step()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        s_us = 1e3 * s0.elapsed_time(s1) / 50
+        single = {"us_per_call": s_us, "value": CW_PER_SUBJECT[mode] / (s_us * 1e-6), "unit": UNIT,
+                  "note": "one subject = 180.5 MB of raw input, comparable to the 126 MB L2; 50 back-to-back launches"}
+
     # ---- the other two analysis modes over the same resident batch (kernel only; informative, rank 0) ----
     other_modes = {}
     if rank == 0 and not args.skip_other_modes:
@@ -539,7 +562,7 @@ def run_gpu_arm(args):
                     "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
                             "D2H of DE+PSD, 3 streams) -> pinned host features"},
             "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),
-            "roofline": roofline, "fp32_pipe": fp32_pipe, "other_modes": other_modes, "next_rows": next_rows,
+            "roofline": roofline, "fp32_pipe": fp32_pipe, "single_subject": single, "other_modes": other_modes, "next_rows": next_rows,
             "cpu_baseline": cpu,
             "parity": parity,
         }

@@ -282,7 +282,7 @@ namespace eegfe {
 // kSplit == 2: even-sweep warps and odd-sweep warps stage their partial band energies; the storer adds them
 //              and does the epilogue (the same additions, so the result is bit-identical to kSplit == 1).
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, bool NORM>
+template <class C>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -404,26 +404,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           sweep_any<C::kNi, C::kHann, C::kVec>(win, sweep, zero5, va);
         }
       }
-      if constexpr (NORM) {
-        // GLMNet raw branch: the staged clip rows leave again as per-channel normalised float32 clips.  Each warp
-        // of the group takes every kGroupWarps-th row; a row is 100 float4, stored coalesced.
-        static_assert(!NORM || (C::kLoad == 400 && C::kWindows == 7), "normalised clips ride on the 500 ms kernel");
-        for (int r = gt / 32; r < nrows; r += C::kGroupWarps) {
-          const unsigned grow = row0 + r;
-          const unsigned ch = grow % job.n_ch;
-          const float sc = __ldg(job.norm_scale + ch), sh = __ldg(job.norm_shift + ch);
-          const float4* src = reinterpret_cast<const float4*>(ring + s * C::kSlotFloats + r * C::kRowStride);
-          float4* dst = reinterpret_cast<float4*>(job.norm_out + (job.norm_row0 + grow) * 400);
-          for (int i = lane; i < 100; i += 32) {
-            float4 v = src[i];
-            v.x = fmaf(v.x, sc, sh);
-            v.y = fmaf(v.y, sc, sh);
-            v.z = fmaf(v.z, sc, sh);
-            v.w = fmaf(v.w, sc, sh);
-            dst[i] = v;
-          }
-        }
-      }
+      // (Handing the slot back right after the radix-8 stage, two DFT-25 earlier, measured 4 % SLOWER in 1 s mode.)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp no longer reads the input slot
       if constexpr (C::kGroupStore) {
@@ -644,36 +625,22 @@ template <class C>
 static int launch(const Job& job, bool aligned16, cudaStream_t stream)
 {
   if (job.total_rows == 0) return 0;
-#ifndef EEGFE_500MS_RING      // (A/B builds only: -DEEGFE_500MS_RING keeps the 500 ms mode on the ring kernel)
-  if constexpr (C::kLoad == 400 && C::kWindows == 7) {
-    if (aligned16) return launch_stream(job, stream);
-  }
-#endif
   const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (aligned16) {
-    unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
-    if (grid > n_tiles) grid = n_tiles;
     if constexpr (C::kLoad == 400 && C::kWindows == 7) {
-      if (job.norm_out != nullptr) {
-        static bool configured_norm = false;
-        if (!configured_norm) {
-          cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-          if (e != cudaSuccess) return static_cast<int>(e);
-          configured_norm = true;
-        }
-        de_psd_kernel<C, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
-        ++g_launches;
-        return static_cast<int>(cudaGetLastError());
+      return launch_stream(job, stream);                   // 500 ms sliding windows: the streaming kernel
+    } else {
+      if (job.norm_out != nullptr) return EEGFE_EINVAL;
+      unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
+      if (grid > n_tiles) grid = n_tiles;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = true;
       }
+      de_psd_kernel<C><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
     }
-    if (job.norm_out != nullptr) return EEGFE_EINVAL;
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      configured = true;
-    }
-    de_psd_kernel<C, false><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
   } else {
     if (job.norm_out != nullptr) return EEGFE_EINVAL;     // the normalised-clip product needs 16-byte aligned rows
     static bool configured = false;
@@ -1058,11 +1025,7 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 {
   int g = 0, b = 0, s = 0, r = 0;
   switch (mode) {
-#ifndef EEGFE_500MS_RING
     case EEGFE_MODE_500MS: g = 1; b = StreamCfg::kThreads; s = StreamCfg::kSmemBytes; r = StreamCfg::kRows; break;
-#else
-    case EEGFE_MODE_500MS: g = CfgSliding500::kCtasPerSm; b = CfgSliding500::kThreads; s = CfgSliding500::kSmemBytes; r = CfgSliding500::kRows; break;
-#endif
     case EEGFE_MODE_1S: g = CfgOneSec::kCtasPerSm; b = CfgOneSec::kThreads; s = CfgOneSec::kSmemBytes; r = CfgOneSec::kRows; break;
     case EEGFE_MODE_2S: g = CfgTwoSec::kCtasPerSm; b = CfgTwoSec::kThreads; s = CfgTwoSec::kSmemBytes; r = CfgTwoSec::kRows; break;
     default: return EEGFE_EINVAL;
