@@ -82,6 +82,10 @@ struct Cfg {
 //    eegfe_tables.h gives 16 wavefronts per load step (14 ideal, 28 with dense rows and thread = 7 row + window);
 //  * 1 s / 2 s / pre-cut: windows start 16-byte aligned -> LDS.128 with lanes = consecutive rows, conflict-free
 //    iff (row stride / 4) is odd: 404 -> 101, 204 -> 51, 100 -> 25.
+// Group count: the 1 s kernels are where FFT work and HBM traffic are closest to balance (the memory pipeline alone
+// reaches 94 % of the measured HBM peak there, with the FFT 83 %); a fifth worker group (156 registers x 384 threads)
+// closes half of that gap (87 %).  The 2 s kernel is bounded by its access pattern (800 B out of every 1600 B: 83 %
+// with or without the FFT), so it keeps four.
 // Ring sizing: the 500 ms kernel is FP32-bound (one tile of prefetch per group is plenty) and its 224-thread group
 // leaves the producer warp time to double as the storer.  The 1 s / 2 s / pre-cut kernels are HBM-bound at 800 B
 // (400 B) per channel-window and want ~100 KB per SM in flight, hence small tiles, four groups and as many surplus
@@ -91,10 +95,10 @@ struct Cfg {
 // 32 copies of 800 B per 26 KB tile keep one warp busy ~0.5 us: two producer warps where rows are short.
 //                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP GSTORE PROD
 using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, false, 1>;  // 224 + 32 thr, 110 KB x 2
-using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 4, 8, 1, 4, 4, 2, false, true, 2>;  // 4 x 64 + 64 thr, 212 KB
+using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 5, 8, 1, 4, 4, 2, false, true, 2>;  // 5 x 64 + 64 thr, 214 KB
 using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, true, 2>;    // 4 x 64 + 64 (samples 0..199)
 using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, true, 2>;   // 4 x 64 + 64, pre-cut 500 ms
-using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 4, 8, 1, 4, 4, 2, false, true, 2>;    // 4 x 64 + 64, pre-cut 1 s
+using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 5, 8, 1, 4, 4, 2, false, true, 2>;    // 5 x 64 + 64, pre-cut 1 s
 
 __constant__ unsigned char c_lane_map_500[224] = {EEGFE_LANE_MAP_500};
 
@@ -293,6 +297,11 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   // rematerialises the lane-map look-up, an indexed constant load with ~1 us of latency, twice per tile).
   int* const thread_meta = reinterpret_cast<int*>(out_stage + C::kGroups * 2 * C::kOutFloats);   // [kWorkers]
   __shared__ uint64_t full_bar[C::kSlots], empty_bar[C::kSlots], out_full_bar[C::kGroups], out_empty_bar[C::kGroups];
+  // armed[s] = number of tiles whose copies have been ISSUED into slot s.  A parity wait on full[s] only tells
+  // "phase k" from "phase k - 2" if the waiter is at most one phase ahead of the barrier; worker groups advance
+  // independently, so a group can reach tile m before the slot's previous tile (m - kSlots, another group's unless
+  // kSlots % kGroups == 0) has even been requested.  Waiting for armed[s] > k first makes the parity wait unambiguous.
+  __shared__ unsigned armed[C::kSlots];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -317,6 +326,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
     for (int s = 0; s < C::kSlots; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], C::kGroupWarps);
+      armed[s] = 0;
     }
 #pragma unroll
     for (int g = 0; g < C::kGroups; ++g) {
@@ -348,7 +358,10 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
         if (free_slot) {
           const unsigned row0 = tile_row0(m);
           const unsigned nrows = tile_nrows(row0);
-          if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
+            st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
+          }
           __syncwarp();
           for (unsigned r = lane; r < nrows; r += 32) {
             const long long off = row_offset(job, row0 + r, C::kWindows, nullptr);
@@ -387,6 +400,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
     int j = 0;                                         // this group's j-th tile
     for (int m = g; m < n_mine; m += C::kGroups, ++j) {
       const int s = m % C::kSlots;
+      while (ld_acquire_smem(&armed[s]) <= static_cast<unsigned>(m / C::kSlots)) __nanosleep(20);
       mbar_wait(&full_bar[s], (m / C::kSlots) & 1);
       const unsigned row0 = tile_row0(m);
       const int nrows = tile_nrows(row0);
@@ -394,6 +408,12 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       const bool live = (meta >> 25) < nrows;
       const float* win = ring + s * C::kSlotFloats + (meta & 0x3fff);
       float va[5], vb[5];
+#ifdef EEGFE_NOCOMPUTE      // (measurement builds only: the memory pipeline without the FFT -- one sample per window)
+      if (live) {
+#pragma unroll
+        for (int b = 0; b < 5; ++b) va[b] = vb[b] = win[b * 4];
+      }
+#else
       if (live) {
         if constexpr (C::kSplit == 1) {
           float e[5];
@@ -404,6 +424,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           sweep_any<C::kNi, C::kHann, C::kVec>(win, sweep, zero5, va);
         }
       }
+#endif
       // (Handing the slot back right after the radix-8 stage, two DFT-25 earlier, measured 4 % SLOWER in 1 s mode.)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp no longer reads the input slot

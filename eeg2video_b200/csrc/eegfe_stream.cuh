@@ -79,12 +79,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // builds the out-of-line form for comparison.
 
 // whole warp: re-arm `bar` and issue one bulk copy per row of the tile starting at global row `row0`
-__device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot, uint64_t* bar, unsigned row0, int nrows)
+__device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
+                                                   unsigned generation, unsigned row0, int nrows)
 {
   const Job& job = *jobp;
   const int lane = threadIdx.x & 31;
   fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy refill
-  if (lane == 0) mbar_arrive_expect_tx(bar, nrows * StreamCfg::kRowBytes);
+  if (lane == 0) {
+    mbar_arrive_expect_tx(bar, nrows * StreamCfg::kRowBytes);
+    st_release_smem(armed, generation + 1u);            // see `armed` in the kernel
+  }
   __syncwarp();
   if (lane < nrows) {
     const long long off = row_offset(job, row0 + lane, StreamCfg::kWindows, nullptr);
@@ -138,6 +142,11 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
   int* const unit_meta = reinterpret_cast<int*>(stage + C::kSlots * 2 * C::kOutFloats);   // [kUnits]
   __shared__ uint64_t full_bar[C::kSlots];
   __shared__ unsigned consumed[C::kSlots], staged[C::kSlots], drained[C::kSlots];
+  // armed[s] = number of tiles whose copies have been ISSUED into slot s.  A parity wait on full[s] cannot tell
+  // "generation k landed" from "generation k - 2 landed"; a warp that got far ahead of a straggler could reach
+  // generation k of a slot before generation k - 1 has even been requested.  Waiting for armed[s] > k first
+  // (the barrier is then in phase k or beyond) makes the parity wait unambiguous.
+  __shared__ unsigned armed[C::kSlots];
   __shared__ unsigned next_pass;
 
   const int tid = threadIdx.x;
@@ -164,6 +173,7 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
       consumed[s] = 0;
       staged[s] = 0;
       drained[s] = 0;
+      armed[s] = 0;
     }
     next_pass = 0;
     mbar_fence_init();
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
     const unsigned w = tid >> 5;
     if (w < C::kSlots && w < n_mine) {
       const unsigned row0 = tile_row0(w);
-      stream_load_tile(&job, ring + w * C::kSlotFloats, &full_bar[w], row0, tile_nrows(row0));
+      stream_load_tile(&job, ring + w * C::kSlotFloats, &full_bar[w], &armed[w], 0u, row0, tile_nrows(row0));
     }
   }
 
@@ -201,8 +211,12 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
     {
       locate();
       const unsigned t0 = __shfl_sync(0xffffffffu, t, 0), t1 = __shfl_sync(0xffffffffu, t, 16);
+      while (ld_acquire_smem(&armed[t0 % C::kSlots]) <= t0 / C::kSlots) __nanosleep(20);
       mbar_wait(&full_bar[t0 % C::kSlots], (t0 / C::kSlots) & 1);
-      if (t1 != t0) mbar_wait(&full_bar[t1 % C::kSlots], (t1 / C::kSlots) & 1);
+      if (t1 != t0) {
+        while (ld_acquire_smem(&armed[t1 % C::kSlots]) <= t1 / C::kSlots) __nanosleep(20);
+        mbar_wait(&full_bar[t1 % C::kSlots], (t1 / C::kSlots) & 1);
+      }
       live = valid && (meta >> 25) < tile_nrows(tile_row0(t));
       if constexpr (NORM) {
         if (valid) {
@@ -253,7 +267,8 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
       if (last & 1u) {
         if (tk + C::kSlots < n_mine) {
           const unsigned r0 = tile_row0(tk + C::kSlots);
-          stream_load_tile(&job, ring + sk * C::kSlotFloats, &full_bar[sk], r0, tile_nrows(r0));
+          stream_load_tile(&job, ring + sk * C::kSlotFloats, &full_bar[sk], &armed[sk], tk / C::kSlots + 1, r0,
+                           tile_nrows(r0));
         }
       }
       if (last & 2u) {

@@ -405,3 +405,18 @@ def test_script_entry_points_follow_the_reference_layout(tmp_path, monkeypatch):
     assert not (pre / "DE_500ms_sw" / "sub1.npy").exists()                        # --subs 2 only
     de_ref, _ = oracle.de_psd_closed_form(wins[0, 0], 200, 0.5)
     assert np.max(np.abs(de5[0, 0] - de_ref)) <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ("500ms", "1s", "2s"))
+def test_repeated_launches_are_bit_identical(mode):
+    """Race canary: 40 launches on batches of varying size (different tiles per CTA, different tails) must all
+    reproduce the same bits.  (A fifth worker group in the 1 s ring kernel once corrupted one tile in ~7 % of the
+    launches: worker groups waited on an mbarrier parity two phases ahead -- tools/stress.py is the long form.)"""
+    raw = synth.synth_cohort(range(4), DEV).reshape(28, 62, 104000)
+    mid = frontend.MODES[mode]
+    cands = [ops.de_psd_from_raw(raw, mid) for _ in range(3)]
+    ref = cands[0] if torch.equal(cands[0][0], cands[1][0]) or torch.equal(cands[0][0], cands[2][0]) else cands[1]
+    for i in range(40):
+        n = 28 - (i % 5)
+        de, psd, _ = ops.de_psd_from_raw(raw[:n], mid)
+        assert torch.equal(de, ref[0][:n * 200]) and torch.equal(psd, ref[1][:n * 200]), f"launch {i}"
