@@ -82,10 +82,12 @@ struct Cfg {
 //    eegfe_tables.h gives 16 wavefronts per load step (14 ideal, 28 with dense rows and thread = 7 row + window);
 //  * 1 s / 2 s / pre-cut: windows start 16-byte aligned -> LDS.128 with lanes = consecutive rows, conflict-free
 //    iff (row stride / 4) is odd: 404 -> 101, 204 -> 51, 100 -> 25.
-// Group count: the 1 s kernels are where FFT work and HBM traffic are closest to balance (the memory pipeline alone
-// reaches 94 % of the measured HBM peak there, with the FFT 83 %); a fifth worker group (156 registers x 384 threads)
-// closes half of that gap (87 %).  The 2 s kernel is bounded by its access pattern (800 B out of every 1600 B: 83 %
-// with or without the FFT), so it keeps four.
+// Group count: the 1 s kernels are where FFT work and HBM traffic are closest to balance: the memory pipeline alone
+// (-DEEGFE_NOCOMPUTE) reaches 94 % of the measured HBM peak there, with four worker groups the full kernel 83 %.
+// Seven groups (14 worker + 2 producer warps = 16 warps at 128 registers, no spills in the split-sweep form) keep the
+// FP32 pipe fed while other groups wait at their store barriers: 5 groups 87 %, 6 groups 97 %, 7 groups 100 % of the
+// (copy-measured) HBM peak.  The 2 s kernel is bounded by its access pattern instead -- 800 B out of every 1600 B, which
+// L2 rounds up to 896 B of 128-byte lines: 83 % with or without the FFT -- and keeps four groups.
 // Ring sizing: the 500 ms kernel is FP32-bound (one tile of prefetch per group is plenty) and its 224-thread group
 // leaves the producer warp time to double as the storer.  The 1 s / 2 s / pre-cut kernels are HBM-bound at 800 B
 // (400 B) per channel-window and want ~100 KB per SM in flight, hence small tiles, four groups and as many surplus
@@ -95,10 +97,10 @@ struct Cfg {
 // 32 copies of 800 B per 26 KB tile keep one warp busy ~0.5 us: two producer warps where rows are short.
 //                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP GSTORE PROD
 using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, false, 1>;  // 224 + 32 thr, 110 KB x 2
-using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 5, 8, 1, 4, 4, 2, false, true, 2>;  // 5 x 64 + 64 thr, 214 KB
+using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 7, 8, 1, 4, 4, 2, false, true, 2>;  // 7 x 64 + 64 thr, 218 KB
 using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, true, 2>;    // 4 x 64 + 64 (samples 0..199)
 using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, true, 2>;   // 4 x 64 + 64, pre-cut 500 ms
-using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 5, 8, 1, 4, 4, 2, false, true, 2>;    // 5 x 64 + 64, pre-cut 1 s
+using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 7, 8, 1, 4, 4, 2, false, true, 2>;    // 7 x 64 + 64, pre-cut 1 s
 
 __constant__ unsigned char c_lane_map_500[224] = {EEGFE_LANE_MAP_500};
 
