@@ -35,8 +35,18 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--launches", type=int, default=20)
     ap.add_argument("--peak", type=float, default=6541.8)
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128), 0 = leave")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    torch.cuda.init()
+    if args.l2_fetch:
+        rt = ctypes.CDLL("libcudart.so.12")
+        val = ctypes.c_size_t()
+        rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(args.l2_fetch))
+        val2 = ctypes.c_size_t()
+        rt.cudaDeviceGetLimit(ctypes.byref(val2), 5)
+        print(f"cudaLimitMaxL2FetchGranularity {val.value} -> {val2.value} (rc {rc})")
     n_blocks, n_ch, t_len = args.subjects * 7, 62, 104000
     g = torch.Generator(device=dev).manual_seed(1)
     raw = torch.randn((n_blocks, n_ch, t_len), device=dev, generator=g) * 30.0
