@@ -401,6 +401,32 @@ def run_gpu_arm(args):
             other_modes[om] = {"value": o_cw / (o_ms * 1e-3), "unit": UNIT, "kernel_ms": o_ms,
                                "hbm_gbs": o_gbs, "hbm_frac": o_gbs / measured_peaks()[0], "kernel": KERNEL_NAME[om]}
             del o_de, o_psd
+        # BASELINE configs[1], second entry: the reference's own call pattern, DE_PSD on MATERIALISED
+        # 500 ms windows (S, 7, 40, 5, 7, 62, 100) -- 440 B per channel-window instead of the fused 268.6 B
+        clips_all = ops.segment_clips(raw, 200)
+        wins = ops.sliding_windows(clips_all).reshape(-1, 100)
+        del clips_all
+        w_de = torch.empty((wins.shape[0], 5), dtype=torch.float32, device=dev)
+        w_psd = torch.empty_like(w_de)
+
+        def w_step():
+            _lib.check(lib.eegfe_de_psd_windows(wins.data_ptr(), wins.shape[0], 100, 100, w_de.data_ptr(),
+                                                w_psd.data_ptr(), status.data_ptr(), stream.cuda_stream))
+        for _ in range(3):
+            w_step()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record(stream)
+        for _ in range(args.steps):
+            w_step()
+        o1.record(stream)
+        torch.cuda.synchronize()
+        o_ms = o0.elapsed_time(o1) / args.steps
+        o_gbs = wins.shape[0] * 440.0 / (o_ms * 1e-3) / 1e9
+        other_modes["500ms_precut_windows"] = {
+            "value": wins.shape[0] / (o_ms * 1e-3), "unit": UNIT, "kernel_ms": o_ms, "hbm_gbs": o_gbs,
+            "hbm_frac": o_gbs / measured_peaks()[0], "algorithmic_bytes_per_channel_window": 440.0,
+            "kernel": "eegfe::de_psd_stream_kernel<StreamCfgWin100> (eegfe_de_psd_windows)"}
+        del wins, w_de, w_psd
 
     # ---- next row: GLMNet input build = normalised 2 s clips + 500 ms features in one pass ----
     next_rows = {}

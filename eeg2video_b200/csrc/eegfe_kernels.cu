@@ -205,7 +205,8 @@ __device__ __forceinline__ bool store_tile(const Job& job, const float* out_a, c
     const unsigned g = row0 + ra;
     const unsigned u = g / job.n_ch;
     const int ch = static_cast<int>(g - u * job.n_ch);
-    const int seg = min(nrows - ra, static_cast<int>(job.n_ch) - ch);
+    // one window per row: [clip][channel][band] is contiguous across clips too -> the whole tile is a single run
+    const int seg = C::kWindows == 1 ? nrows : min(nrows - ra, static_cast<int>(job.n_ch) - ch);
     const int n = seg * 5;
     const int obase = static_cast<int>((u * C::kWindows * job.n_ch + ch) * 5u);
     const float* sa = out_a + ra * 5 + t;
@@ -619,26 +620,32 @@ static int sm_count()
 }
 
 // 500 ms mode, 16-byte aligned rows: the streaming kernel (eegfe_stream.cuh), one CTA of 16 warps per SM.
+template <class SC>
 static int launch_stream(const Job& job, cudaStream_t stream)
 {
   if (job.total_rows == 0) return 0;
-  const unsigned n_tiles = (job.total_rows + StreamCfg::kRows - 1) / StreamCfg::kRows;
+  const unsigned n_tiles = (job.total_rows + SC::kRows - 1) / SC::kRows;
   unsigned grid = static_cast<unsigned>(sm_count());
   if (grid > n_tiles) grid = n_tiles;
+  constexpr bool kCanNorm = SC::kLoad == 400 && SC::kWindows == 7;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(de_psd_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         StreamCfg::kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(de_psd_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               StreamCfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(de_psd_stream_kernel<SC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SC::kSmemBytes);
+    if constexpr (kCanNorm) {
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(de_psd_stream_kernel<SC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SC::kSmemBytes);
+    }
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  if (job.norm_out != nullptr)
-    de_psd_stream_kernel<true><<<grid, StreamCfg::kThreads, StreamCfg::kSmemBytes, stream>>>(job);
-  else
-    de_psd_stream_kernel<false><<<grid, StreamCfg::kThreads, StreamCfg::kSmemBytes, stream>>>(job);
+  if (job.norm_out != nullptr) {
+    if constexpr (kCanNorm) de_psd_stream_kernel<SC, true><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
+    else return EEGFE_EINVAL;
+  } else {
+    de_psd_stream_kernel<SC, false><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
+  }
   ++g_launches;
   return static_cast<int>(cudaGetLastError());
 }
@@ -651,7 +658,9 @@ static int launch(const Job& job, bool aligned16, cudaStream_t stream)
   const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (aligned16) {
     if constexpr (C::kLoad == 400 && C::kWindows == 7) {
-      return launch_stream(job, stream);                   // 500 ms sliding windows: the streaming kernel
+      return launch_stream<StreamCfg>(job, stream);        // 500 ms sliding windows: the streaming kernel
+    } else if constexpr (C::kLoad == 100 && C::kWindows == 1) {
+      return launch_stream<StreamCfgWin100>(job, stream);  // pre-cut 500 ms windows: the streaming kernel, dense rows
     } else {
       if (job.norm_out != nullptr) return EEGFE_EINVAL;
       unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;

@@ -32,24 +32,35 @@ namespace eegfe {
 #ifndef EEGFE_STREAM_WARPS
 #define EEGFE_STREAM_WARPS 16
 #endif
-struct StreamCfg {
-  static constexpr int kRows = 16;            // rows per tile
-  static constexpr int kWindows = 7;
-  static constexpr int kHop = 50;
-  static constexpr int kLoad = 400;
-  static constexpr int kRowStride = 404;      // floats; bank skew, see Cfg
+template <int ROWS_, int WINDOWS_, int HOP_, int LOAD_, int STRIDE_, int VEC_, int SLOTS_, bool LANEMAP_>
+struct StreamCfgT {
+  static constexpr int kRows = ROWS_;          // rows per tile
+  static constexpr int kWindows = WINDOWS_;    // analysis windows per row
+  static constexpr int kHop = HOP_;
+  static constexpr int kLoad = LOAD_;          // samples fetched per row
+  static constexpr int kRowStride = STRIDE_;   // floats between rows in shared memory (bank skew, see Cfg)
+  static constexpr int kVec = VEC_;            // floats per shared-memory load
+  static constexpr bool kLaneMap = LANEMAP_;   // unit order inside a tile through c_lane_map_500_r16
   static constexpr int kRowBytes = kLoad * 4;
-  static constexpr int kSlots = 7;
+  static constexpr int kSlots = SLOTS_;
   static constexpr int kWarps = EEGFE_STREAM_WARPS;
   static constexpr int kThreads = kWarps * 32;
-  static constexpr int kUnits = kRows * kWindows;          // 112
-  static constexpr int kHalfPasses = kUnits / 16;          // 7
+  static constexpr int kUnits = kRows * kWindows;          // channel-windows per tile
+  static constexpr int kHalfPasses = kUnits / 16;
   static constexpr int kSlotFloats = kRows * kRowStride;
   static constexpr int kOutFloats = kUnits * 5;            // per staging array
   static constexpr int kSplit = 1;                         // store_tile: staged values are final (de, psd)
   static constexpr int kSmemBytes = (kSlots * (kSlotFloats + 2 * kOutFloats) + kUnits) * 4;
+  static_assert(kUnits % 16 == 0, "a tile is a whole number of half-passes");
+  static_assert(kRowBytes % 16 == 0 && kRowStride % 4 == 0, "TMA bulk copies need 16-byte aligned rows");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
+// 500 ms windows sliding over 2 s clip rows (fused segmentation): 16 rows x 7 windows, LDS.64 + lane map
+using StreamCfg = StreamCfgT<16, 7, 50, 400, 404, 2, 7, true>;
+// pre-cut 500 ms windows (the reference's own call pattern, DE_PSD on a materialised (.., 100) array): 64 rows of 100
+// samples, dense rows (LDS.128 over consecutive rows is conflict-free because 100 / 4 = 25 is odd); a tile of
+// contiguous rows arrives with ONE bulk copy.
+using StreamCfgWin100 = StreamCfgT<64, 1, 0, 100, 100, 4, 7, false>;
 
 __constant__ unsigned char c_lane_map_500_r16[112] = {EEGFE_LANE_MAP_500_R16};
 
@@ -78,7 +89,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // constants cannot stay live across a call and are re-materialised every pass); -DEEGFE_STREAM_DUTY=__noinline__
 // builds the out-of-line form for comparison.
 
-// whole warp: re-arm `bar` and issue one bulk copy per row of the tile starting at global row `row0`
+// whole warp: re-arm `bar` and issue the bulk copies of the tile starting at global row `row0`: one per row, or a
+// single one when the rows sit back to back in HBM exactly as they do in the slot (pre-cut windows, dense array)
+template <class SC>
 __device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
                                                    unsigned generation, unsigned row0, int nrows)
 {
@@ -86,21 +99,27 @@ __device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot,
   const int lane = threadIdx.x & 31;
   fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy refill
   if (lane == 0) {
-    mbar_arrive_expect_tx(bar, nrows * StreamCfg::kRowBytes);
+    mbar_arrive_expect_tx(bar, nrows * SC::kRowBytes);
     st_release_smem(armed, generation + 1u);            // see `armed` in the kernel
   }
   __syncwarp();
-  if (lane < nrows) {
-    const long long off = row_offset(job, row0 + lane, StreamCfg::kWindows, nullptr);
-    bulk_copy_g2s(slot + lane * StreamCfg::kRowStride, job.in + off, StreamCfg::kRowBytes, bar);
+  if (SC::kRowStride == SC::kLoad && job.n_ch == 1 && job.d1 == 1 && job.s0 == SC::kLoad) {
+    if (lane == 0)
+      bulk_copy_g2s(slot, job.in + job.base + static_cast<long long>(row0) * SC::kLoad, nrows * SC::kRowBytes, bar);
+  } else {
+    for (int r = lane; r < nrows; r += 32) {
+      const long long off = row_offset(job, row0 + r, SC::kWindows, nullptr);
+      bulk_copy_g2s(slot + r * SC::kRowStride, job.in + off, SC::kRowBytes, bar);
+    }
   }
   __syncwarp();
 }
 
 // whole warp: staged tile -> HBM
+template <class SC>
 __device__ EEGFE_STREAM_DUTY void stream_store_tile(const Job* jobp, const float* out_a, unsigned row0, int nrows)
 {
-  store_tile<StreamCfg, 32>(*jobp, out_a, out_a + StreamCfg::kOutFloats, row0, nrows, threadIdx.x & 31);
+  store_tile<SC, 32>(*jobp, out_a, out_a + SC::kOutFloats, row0, nrows, threadIdx.x & 31);
   __syncwarp();
 }
 
@@ -132,10 +151,11 @@ __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const flo
   }
 }
 
-template <bool NORM>
-__global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(const __grid_constant__ Job job)
+template <class SC, bool NORM>
+__global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __grid_constant__ Job job)
 {
-  using C = StreamCfg;
+  using C = SC;
+  static_assert(!NORM || (C::kLoad == 400 && C::kWindows == 7), "normalised clips ride on the sliding 500 ms form");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const ring = reinterpret_cast<float*>(smem_raw);                     // [slot][row][kRowStride]
   float* const stage = ring + C::kSlots * C::kSlotFloats;                      // [slot][de | psd][window][row][band]
@@ -161,8 +181,13 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
   };
 
   if (tid < C::kUnits) {
-    const int code = c_lane_map_500_r16[tid];
-    const int row = code >> 3, w = code & 7;
+    int row = tid, w = 0;
+    if constexpr (C::kLaneMap) {
+      static_assert(!C::kLaneMap || C::kUnits == 112, "lane map of 16-row x 7-window tiles");
+      const int code = c_lane_map_500_r16[tid];
+      row = code >> 3;
+      w = code & 7;
+    }
     // bits 0..13: window offset in the slot (floats), 14..24: staging index, 25..30: row in tile
     unit_meta[tid] = (row * C::kRowStride + w * C::kHop) | (((w * C::kRows + row) * 5) << 14) | (row << 25);
   }
@@ -183,7 +208,7 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
     const unsigned w = tid >> 5;
     if (w < C::kSlots && w < n_mine) {
       const unsigned row0 = tile_row0(w);
-      stream_load_tile(&job, ring + w * C::kSlotFloats, &full_bar[w], &armed[w], 0u, row0, tile_nrows(row0));
+      stream_load_tile<C>(&job, ring + w * C::kSlotFloats, &full_bar[w], &armed[w], 0u, row0, tile_nrows(row0));
     }
   }
 
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
       }
       if (live) {
         float e[5];
-        window_band_energy<4, kHannHalfSec, 2>(ring + s * C::kSlotFloats + (meta & 0x3fff), e);
+        window_band_energy<4, kHannHalfSec, C::kVec>(ring + s * C::kSlotFloats + (meta & 0x3fff), e);
         if (band_features(e, psd, de) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
       }
     }
@@ -267,13 +292,13 @@ __global__ void __launch_bounds__(StreamCfg::kThreads, 1) de_psd_stream_kernel(c
       if (last & 1u) {
         if (tk + C::kSlots < n_mine) {
           const unsigned r0 = tile_row0(tk + C::kSlots);
-          stream_load_tile(&job, ring + sk * C::kSlotFloats, &full_bar[sk], &armed[sk], tk / C::kSlots + 1, r0,
-                           tile_nrows(r0));
+          stream_load_tile<C>(&job, ring + sk * C::kSlotFloats, &full_bar[sk], &armed[sk], tk / C::kSlots + 1, r0,
+                              tile_nrows(r0));
         }
       }
       if (last & 2u) {
         const unsigned r0 = tile_row0(tk);
-        stream_store_tile(&job, stage + sk * 2 * C::kOutFloats, r0, tile_nrows(r0));
+        stream_store_tile<C>(&job, stage + sk * 2 * C::kOutFloats, r0, tile_nrows(r0));
         if (lane == 0) st_release_smem(&drained[sk], tk / C::kSlots + 1);
       }
     }
