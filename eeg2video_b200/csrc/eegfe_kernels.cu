@@ -461,21 +461,33 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
 // same arithmetic for rows that are only 4-byte aligned (odd block lengths / strides): TMA bulk copies need
 // 16-byte alignment, so this variant loads cooperatively, one stage, block barriers.  Correct, not tuned.
 // ---------------------------------------------------------------------------------------------------------------
+// A CTA works on kUnalignedTiles<C> tiles at a time (one sub-group of kUnits threads per tile) so that it has
+// >= 256 threads whatever the tile shape.
 template <class C>
-__global__ void __launch_bounds__(C::kUnits, 1) de_psd_kernel_unaligned(const Job job)
+constexpr int kUnalignedTiles = (256 + C::kUnits - 1) / C::kUnits;
+
+template <class C>
+__global__ void __launch_bounds__(C::kUnits * kUnalignedTiles<C>, 1) de_psd_kernel_unaligned(const Job job)
 {
+  constexpr int M = kUnalignedTiles<C>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* const buf = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int sub = tid / C::kUnits;                       // which of the CTA's M tiles this thread works on
+  const int ut = tid - sub * C::kUnits;
+  float* const buf = reinterpret_cast<float*>(smem_raw) + sub * C::kSlotFloats;
   const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   int row_in_tile, w;
-  unit_to_row_window<C>(tid, row_in_tile, w);
-  for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  unit_to_row_window<C>(ut, row_in_tile, w);
+  for (unsigned tile0 = blockIdx.x * M; tile0 < n_tiles; tile0 += gridDim.x * M) {
+    const unsigned tile = tile0 + sub;
     const unsigned row0 = tile * C::kRows;
-    const unsigned left = job.total_rows - row0;
-    const unsigned nrows = left < C::kRows ? left : C::kRows;
-    for (unsigned r = tid / 32; r < nrows; r += C::kUnits / 32) {
+    unsigned nrows = 0;
+    if (tile < n_tiles) {
+      const unsigned left = job.total_rows - row0;
+      nrows = left < C::kRows ? left : C::kRows;
+    }
+    for (unsigned r = ut / 32; r < nrows; r += C::kUnits / 32) {
       const float* src = job.in + row_offset(job, row0 + r, C::kWindows, nullptr);
       for (int i = lane; i < C::kLoad; i += 32) buf[r * C::kRowStride + i] = __ldg(src + i);
     }
@@ -517,6 +529,32 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const unsigned char* _
     const int v = static_cast<int>(i - row * per_row);
     const unsigned char* s = src + row_offset(geom, static_cast<unsigned>(row), 1, nullptr) * esize;
     reinterpret_cast<vec_t*>(dst + row * row_bytes)[v] = reinterpret_cast<const vec_t*>(s)[v];
+  }
+}
+
+// Rows that are only element-aligned (odd block lengths / strides): one warp per row, consecutive lanes copy
+// consecutive elements -- coalesced on both sides and no per-element index arithmetic (the generic kernel above
+// divides once per element and manages ~1.5 TB/s on such rows).
+template <class T>
+__global__ void __launch_bounds__(256) gather_rows_warp_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                                long long n_rows, int row_elems, Job geom)
+{
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long row = warp; row < n_rows; row += n_warps) {
+    const T* s = src + row_offset(geom, static_cast<unsigned>(row), 1, nullptr);
+    T* d = dst + row * row_elems;
+    for (int i = lane; i < row_elems; i += 128) {
+      T v0 = s[i], v1 = T(), v2 = T(), v3 = T();
+      if (i + 32 < row_elems) v1 = s[i + 32];
+      if (i + 64 < row_elems) v2 = s[i + 64];
+      if (i + 96 < row_elems) v3 = s[i + 96];
+      d[i] = v0;
+      if (i + 32 < row_elems) d[i + 32] = v1;
+      if (i + 64 < row_elems) d[i + 64] = v2;
+      if (i + 96 < row_elems) d[i + 96] = v3;
+    }
   }
 }
 
@@ -676,15 +714,16 @@ static int launch(const Job& job, bool aligned16, cudaStream_t stream)
   } else {
     if (job.norm_out != nullptr) return EEGFE_EINVAL;     // the normalised-clip product needs 16-byte aligned rows
     static bool configured = false;
-    const int smem = C::kSlotFloats * 4;
+    const int smem = C::kSlotFloats * 4 * kUnalignedTiles<C>;
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(de_psd_kernel_unaligned<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return static_cast<int>(e);
       configured = true;
     }
-    unsigned grid = static_cast<unsigned>(sm_count()) * 2;
-    if (grid > n_tiles) grid = n_tiles;
-    de_psd_kernel_unaligned<C><<<grid, C::kUnits, smem, stream>>>(job);
+    unsigned grid = static_cast<unsigned>(sm_count()) * (smem <= 110 * 1024 ? 2 : 1);
+    const unsigned n_groups = (n_tiles + kUnalignedTiles<C> - 1) / kUnalignedTiles<C>;
+    if (grid > n_groups) grid = n_groups;
+    de_psd_kernel_unaligned<C><<<grid, C::kUnits * kUnalignedTiles<C>, smem, stream>>>(job);
   }
   ++g_launches;
   return static_cast<int>(cudaGetLastError());
@@ -955,7 +994,9 @@ int eegfe_segment_clips(const void* raw, int dtype, int64_t n_blocks, int n_ch, 
     unsigned char* dst = static_cast<unsigned char*>(clips) + b0 * rows_per_block * row_bytes;
     if (a16) gather_rows_kernel<16><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
     else if (es == 8) gather_rows_kernel<8><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
-    else if (es == 4) gather_rows_kernel<4><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
+    else if (es == 4)
+      gather_rows_warp_kernel<uint32_t><<<grid, threads, 0, s>>>(reinterpret_cast<const uint32_t*>(src),
+                                                                reinterpret_cast<uint32_t*>(dst), n_rows, 2 * fs, geom);
     else gather_rows_kernel<2><<<grid, threads, 0, s>>>(src, dst, n_rows, row_bytes, es, geom);
     ++g_launches;
     const cudaError_t e = cudaGetLastError();
