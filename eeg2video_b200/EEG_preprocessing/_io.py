@@ -29,8 +29,16 @@ def to_device_f32(x):
     if arr.dtype == object or not (np.issubdtype(arr.dtype, np.floating) or np.issubdtype(arr.dtype, np.integer)
                                    or arr.dtype == np.bool_):
         raise TypeError(f"unsupported dtype {arr.dtype}")
+    if arr.dtype in (np.float64, np.float16, np.int16, np.int32, np.uint8, np.int8, np.int64):
+        # upload in the native type and round to float32 on the device (same round-to-nearest result as numpy's
+        # astype, without a host pass over the recording)
+        if not arr.flags.writeable:
+            arr = arr.copy()
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(device()).to(torch.float32)
     if arr.dtype != np.float32:
         arr = arr.astype(np.float32)
+    if not arr.flags.writeable:
+        arr = arr.copy()
     return torch.from_numpy(np.ascontiguousarray(arr)).to(device())
 
 

@@ -96,7 +96,7 @@ class HostPipeline:
         """raw_host: pinned, contiguous float32 (n_blocks, n_ch, block_len); de_host / psd_host: pinned float32
         feature_shape(n_blocks).  Returns the accumulated status flags (int).  Synchronises before returning."""
         if not (raw_host.is_contiguous() and raw_host.dtype == torch.float32):
-            raise ValueError("raw_host must be contiguous float32")
+            raise ValueError("raw_host must be contiguous float32 (features_from_host converts other types)")
         n_blocks = raw_host.shape[0]
         cb = self.chunk_blocks
         status_all = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -138,7 +138,13 @@ def features_from_host(raw_host, mode="500ms", chunk_blocks=28, device="cuda", c
     lead = raw.shape[:-2]
     flat = raw.reshape((-1,) + tuple(raw.shape[-2:]))
     if flat.dtype != torch.float32:
-        flat = flat.to(torch.float32)
+        # other element types (float64 recordings, int16 codes): block by block through the device, which rounds to
+        # float32 far faster than a host pass; the float32 copy is what the pipeline then streams
+        dev = torch.device(device)
+        out = torch.empty(flat.shape, dtype=torch.float32).pin_memory()
+        for b in range(flat.shape[0]):
+            out[b].copy_(flat[b].to(dev, non_blocking=False).to(torch.float32))
+        flat = out
     if not flat.is_pinned():
         flat = flat.contiguous().pin_memory()
     pipe = HostPipeline(device, flat.shape[1], flat.shape[2], min(chunk_blocks, max(flat.shape[0], 1)), mode, compact)

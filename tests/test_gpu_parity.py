@@ -420,3 +420,20 @@ def test_repeated_launches_are_bit_identical(mode):
         n = 28 - (i % 5)
         de, psd, _ = ops.de_psd_from_raw(raw[:n], mid)
         assert torch.equal(de, ref[0][:n * 200]) and torch.equal(psd, ref[1][:n * 200]), f"launch {i}"
+
+
+def test_float64_and_int16_recordings():
+    """The reference takes whatever dtype the .npy holds; the front end rounds to float32 on the device."""
+    from eeg2video_b200 import pipeline
+    rng = np.random.default_rng(23)
+    raw64 = (30 * rng.standard_normal((2, 5, 104000))).astype(np.float64)
+    want = frontend.de_psd_from_raw(torch.from_numpy(raw64.astype(np.float32)).to(DEV), "1s")
+    de, psd = pipeline.features_from_host(raw64, "1s", device=DEV)
+    assert torch.equal(de, want[0].cpu()) and torch.equal(psd, want[1].cpu())
+    clips64 = oracle.segment_subject(np.concatenate([raw64, np.zeros((5, 5, 104000))]))[:2]
+    de2, psd2 = extract_de_psd_1s(clips64, 200)
+    assert de2.dtype == np.float64 and np.array_equal(de2.astype(np.float32), want[0].cpu().numpy())
+    codes = rng.integers(-3000, 3000, (40, 100)).astype(np.int16)
+    a = DE_PSD(codes, 200, 0.5)
+    b = DE_PSD(codes.astype(np.float64), 200, 0.5)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
