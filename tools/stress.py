@@ -1,19 +1,43 @@
 #!/usr/bin/env python
-"""Determinism / race stress (development tool): every mode, many launches back to back on fresh output buffers,
-each compared bit for bit with the first launch; also against the float64 closed form on one subject.
+"""Determinism / race stress (development tool): every entry point of the feature kernels, many launches back to
+back on batches of varying size (different tiles per CTA, different tails), each compared bit for bit with a
+majority-voted reference launch.
 
-    python tools/stress.py [--subjects 8] [--launches 60]
+    python tools/stress.py [--subjects 8] [--launches 60] [--lib tools/ab/variant.so]
 """
 import argparse
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from eeg2video_b200 import frontend, ops, synth  # noqa: E402
+from eeg2video_b200 import frontend, glmnet_inputs, ops, synth  # noqa: E402
+
+
+def majority(fn):
+    cands = [fn() for _ in range(3)]
+    torch.cuda.synchronize()
+    same01 = all(torch.equal(a, b) for a, b in zip(cands[0], cands[1]))
+    same02 = all(torch.equal(a, b) for a, b in zip(cands[0], cands[2]))
+    return cands[0] if same01 or same02 else cands[1]
+
+
+def run_case(name, launches, make, compare_len):
+    """make(i) -> (outputs tuple, n_leading_units); compare with the reference's leading part."""
+    ref = majority(lambda: make(0)[0])
+    mism = 0
+    for i in range(launches):
+        out, n = make(i)
+        k = compare_len(n)
+        if not all(torch.equal(o, r[:k]) for o, r in zip(out, ref)):
+            mism += 1
+            if mism <= 4:
+                d = (out[0] != ref[0][:k]).nonzero()
+                print(f"  {name}: launch {i} differs at {d.shape[0]} values, first {d[0].tolist()}")
+    print(f"{name}: {launches} launches, {mism} mismatching")
+    return mism
 
 
 def main():
@@ -27,32 +51,33 @@ def main():
         _lib.LIB_PATH = os.path.abspath(args.lib)
     dev = torch.device("cuda:0")
     raw = synth.synth_cohort(range(args.subjects), dev).reshape(args.subjects * 7, 62, 104000)
+    nb = raw.shape[0]
     bad = 0
     for mode in ("500ms", "1s", "2s"):
         mid = frontend.MODES[mode]
-        # reference = majority of three launches (a corrupted first launch must not poison the comparison)
-        cands = [ops.de_psd_from_raw(raw, mid) for _ in range(3)]
-        torch.cuda.synchronize()
-        ref = cands[0] if torch.equal(cands[0][0], cands[1][0]) or torch.equal(cands[0][0], cands[2][0]) else cands[1]
-        mism = 0
-        for i in range(args.launches):
-            # a different sub-batch size every launch changes tiles-per-CTA and the tail
-            n = raw.shape[0] - (i % 5)
-            out = ops.de_psd_from_raw(raw[:n], mid)
-            k = n * 200
-            if not (torch.equal(out[0], ref[0][:k]) and torch.equal(out[1], ref[1][:k])):
-                mism += 1
-                d = (out[0] != ref[0][:k]).nonzero()
-                if mism <= 8:
-                    first = tuple(d[0].tolist())
-                    v = out[0][first]
-                    src = (ref[0] == v).nonzero()
-                    rows = sorted({int(r[0]) * out[0].shape[2] + int(r[2]) for r in d.tolist()})
-                    print(f"  {mode}: launch {i} (n_blocks {n}) differs at {d.shape[0]} values, first {list(first)} "
-                          f"(global rows {rows[0]}..{rows[-1]}, tile {rows[0] // 16}); value {float(v):.6f} vs "
-                          f"{float(ref[0][first]):.6f}; the bad value occurs in the reference at {src[:3].tolist()}")
-        print(f"{mode}: {args.launches} launches, {mism} mismatching")
-        bad += mism
+        bad += run_case(f"from_raw {mode}", args.launches,
+                        lambda i: (ops.de_psd_from_raw(raw[:nb - (i % 5)], mid)[:2], nb - (i % 5)),
+                        lambda n: n * 200)
+    clips = ops.segment_clips(raw[:7], 200)                              # (1400, 62, 400)
+    for mode in ("500ms", "1s", "2s"):
+        mid = frontend.MODES[mode]
+        bad += run_case(f"from_clips {mode}", args.launches,
+                        lambda i: (ops.de_psd_from_clips(clips[:1400 - 37 * (i % 7)], mid)[:2], 1400 - 37 * (i % 7)),
+                        lambda n: n)
+    wins = ops.sliding_windows(clips[:400]).reshape(-1, 100)             # 173600 pre-cut windows
+    bad += run_case("windows 100", args.launches,
+                    lambda i: (ops.de_psd_windows(wins[:wins.shape[0] - 1001 * (i % 6)])[:2], wins.shape[0] - 1001 * (i % 6)),
+                    lambda n: n)
+    w200 = clips[:300].reshape(-1, 200)
+    bad += run_case("windows 200", args.launches,
+                    lambda i: (ops.de_psd_windows(w200[:w200.shape[0] - 333 * (i % 6)])[:2], w200.shape[0] - 333 * (i % 6)),
+                    lambda n: n)
+    mean, std = glmnet_inputs.channel_stats(raw, None)
+    scale = (1.0 / std).float().contiguous()
+    shift = (-mean / std).float().contiguous()
+    bad += run_case("glmnet inputs", max(10, args.launches // 3),
+                    lambda i: (ops.glmnet_inputs_from_raw(raw[:14 - (i % 3)], scale, shift)[:3], 14 - (i % 3)),
+                    lambda n: n * 200)
     sys.exit(1 if bad else 0)
 
 
