@@ -437,3 +437,41 @@ def test_float64_and_int16_recordings():
     a = DE_PSD(codes, 200, 0.5)
     b = DE_PSD(codes.astype(np.float64), 200, 0.5)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_nan_samples_stay_local_like_the_reference():
+    """A NaN sample poisons exactly the channel-windows that contain it (the reference: NaN through the FFT, math.log(nan)
+    = nan, no exception); every other channel-window is unchanged."""
+    rng = np.random.default_rng(29)
+    clips = (30 * rng.standard_normal((3, 4, 400))).astype(np.float32)
+    clean = frontend.de_psd_from_clips(torch.from_numpy(clips).to(DEV), "500ms")
+    clips[1, 2, 120] = np.nan                                       # inside windows 1 and 2 (50..149, 100..199) of clip 1, ch 2
+    de, psd = frontend.de_psd_from_clips(torch.from_numpy(clips).to(DEV), "500ms")
+    bad = torch.isnan(de).any(dim=-1)
+    want = torch.zeros_like(bad)
+    want[1, 1, 2] = want[1, 2, 2] = True
+    assert torch.equal(bad, want) and torch.equal(torch.isnan(psd).any(dim=-1), want)
+    assert torch.equal(de[~bad], clean[0][~bad])
+    de_ref, psd_ref = oracle.de_psd_loop(clips[1, :, 50:150], 200, 0.5)
+    assert np.isnan(de_ref[2]).all() and not np.isnan(de_ref[[0, 1, 3]]).any()
+
+
+def test_jobs_larger_than_32_bit_indexing():
+    """5000 blocks = 1 000 000 clips = 2.17e9 feature values per array: the launcher must split the job (row and
+    output indices are 32-bit inside the kernels).  All blocks alias one recording (block stride 0), so every block's
+    features must equal block 0's."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24e9:
+        pytest.skip("needs ~18 GB of free device memory")
+    one = synth.synth_blocks(1, 41, device=DEV)                       # (1, 62, 104000)
+    de, psd, status = ops.de_psd_from_raw(one.expand(5000, 62, 104000), _lib.MODE_500MS)
+    assert de.shape[0] == 1_000_000 and de.numel() > 2 ** 31
+    ref_de, ref_psd, _ = ops.de_psd_from_raw(one, _lib.MODE_500MS)
+    de = de.reshape(5000, 200, 7, 62, 5)
+    psd = psd.reshape(5000, 200, 7, 62, 5)
+    for b in (0, 1, 4947, 4948, 4949, 4999):                         # 4948 blocks fit one launch; the seam is at 4948
+        assert torch.equal(de[b], ref_de) and torch.equal(psd[b], ref_psd), b
+    assert bool((de == ref_de.unsqueeze(0)).all())
+    assert int(status.item()) == 0
+    del de, psd
+    torch.cuda.empty_cache()
