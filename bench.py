@@ -584,6 +584,8 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes(S * 7)),
                     "d2h_bytes_per_step": int(2 * de_host.numel() * 4), "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_result": e2e_ok,
+                    "h2d_gbs_per_gpu": pipe.h2d_bytes(S * 7) / (e2e_s / e2e_steps) / 1e9,
+                    "bound": "host-to-device copy of the live samples (PCIe Gen5 x16, ~55 GB/s per GPU in practice)",
                     "rank0_numa_cpus": None if numa_cpus is None else len(numa_cpus),
                     "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
                             "D2H of DE+PSD, 3 streams) -> pinned host features"},
