@@ -42,7 +42,7 @@ struct Job {
 
 // per-mode compile-time geometry
 template <int LOAD_, int NWIN_, int HOP_, int NI_, int HANN_, int ROWS_, int GROUPS_, int SLOTS_, int CTAS_, int PAD_,
-          int VEC_, int SPLIT_, bool LANEMAP_, bool GSTORE_, int PRODUCERS_>
+          int VEC_, int SPLIT_, bool LANEMAP_, int PRODUCERS_>
 struct Cfg {
   static constexpr int kLoad = LOAD_;        // samples fetched per row
   static constexpr int kWindows = NWIN_;     // analysis windows per row
@@ -57,7 +57,6 @@ struct Cfg {
   static constexpr int kVec = VEC_;          // floats per shared-memory load (2: LDS.64, 4: LDS.128)
   static constexpr int kSplit = SPLIT_;      // threads per channel-window (2: even / odd sweep in different warps)
   static constexpr bool kLaneMap = LANEMAP_; // thread -> (row, window) through c_lane_map_500
-  static constexpr bool kGroupStore = GSTORE_;  // features are written out by the group itself, not the producer warp
   static constexpr int kUnits = ROWS_ * NWIN_;                 // channel-windows per tile
   static constexpr int kGroupThreads = kUnits * SPLIT_;        // worker threads per group
   static constexpr int kGroupWarps = kGroupThreads / 32;
@@ -71,9 +70,7 @@ struct Cfg {
   static_assert(kUnits % 32 == 0, "a tile must fill whole warps");
   static_assert(kRowBytes % 16 == 0 && kRowStride % 4 == 0, "TMA bulk copies need 16-byte aligned rows");
   static_assert(SPLIT_ == 1 || SPLIT_ == 2, "one or two threads per channel-window");
-  static_assert(SPLIT_ == 1 || GSTORE_, "split sweeps are combined by the group");
   static_assert(GROUPS_ <= 15, "one named barrier per group");
-  static_assert(PRODUCERS_ == 1 || GSTORE_, "the storer role is tied to a single producer warp");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
 // Shared-memory bank rules behind PAD / VEC (B200: 32 banks x 4 B; 64-bit loads are served per half-warp,
@@ -88,19 +85,18 @@ struct Cfg {
 // FP32 pipe fed while other groups wait at their store barriers: 5 groups 87 %, 6 groups 97 %, 7 groups 100 % of the
 // (copy-measured) HBM peak.  The 2 s kernel is bounded by its access pattern instead -- 800 B out of every 1600 B, which
 // L2 rounds up to 896 B of 128-byte lines: 83 % with or without the FFT -- and keeps four groups.
-// Ring sizing: the 500 ms kernel is FP32-bound (one tile of prefetch per group is plenty) and its 224-thread group
-// leaves the producer warp time to double as the storer.  The 1 s / 2 s / pre-cut kernels are HBM-bound at 800 B
-// (400 B) per channel-window and want ~100 KB per SM in flight, hence small tiles, four groups and as many surplus
-// slots as shared memory holds; a tile is due every ~1 us per SM there, too fast for one warp to also write the
-// features, so each group stores its own tile (kGroupStore) and the producers only issue copies.  One bulk copy
-// per row costs a producer warp ~30 issue cycles (the TMA operands are per-lane, the instruction is uniform), so
-// 32 copies of 800 B per 26 KB tile keep one warp busy ~0.5 us: two producer warps where rows are short.
-//                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP GSTORE PROD
-using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, false, 1>;  // 224 + 32 thr, 110 KB x 2
-using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 7, 8, 1, 4, 4, 2, false, true, 2>;  // 7 x 64 + 64 thr, 218 KB
-using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, true, 2>;    // 4 x 64 + 64 (samples 0..199)
-using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, true, 2>;   // 4 x 64 + 64, pre-cut 500 ms
-using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 7, 8, 1, 4, 4, 2, false, true, 2>;    // 7 x 64 + 64, pre-cut 1 s
+// Ring sizing: these kernels are HBM-bound at 800 B (400 B) per channel-window and want ~100 KB per SM in flight, hence
+// small tiles and as many surplus slots as shared memory holds; a tile is due every ~1 us per SM, so each group writes
+// its own tile and the producers only issue copies.  One bulk copy per row costs a producer warp ~30 issue cycles
+// (the TMA operands are per-lane, the instruction is uniform): two producer warps.
+// CfgSliding500 / CfgWin100 only parameterise the unaligned-row fallback kernel: with 16-byte aligned rows those two
+// shapes run on the streaming kernel (eegfe_stream.cuh).
+//                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP PROD
+using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, 1>;
+using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 7, 8, 1, 4, 4, 2, false, 2>;  // 7 x 64 + 64 thr, 218 KB
+using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, 2>;    // 4 x 64 + 64 (samples 0..199)
+using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, 2>;
+using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 7, 8, 1, 4, 4, 2, false, 2>;    // 7 x 64 + 64, pre-cut 1 s
 
 __constant__ unsigned char c_lane_map_500[224] = {EEGFE_LANE_MAP_500};
 
@@ -133,18 +129,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (!done);
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)     // non-blocking phase test
-{
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return done != 0;
 }
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
@@ -273,21 +257,22 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
 namespace eegfe {
 
 // ---------------------------------------------------------------------------------------------------------------
-// the fused kernel (rows 16-byte aligned): warp-specialised, no block-wide barrier in the steady state
+// the ring kernel (rows 16-byte aligned; 1 s / 2 s modes, pre-cut 1 s windows): warp-specialised, no block-wide
+// barrier in the steady state
 //
 // A CTA walks its tiles m = 0, 1, 2, ... (global tile blockIdx.x + m * gridDim.x).  Tile m lands in ring slot
 // m % kSlots and is processed by worker group m % kGroups.
 //
-//   producer warp : for m = 0, 1, ...   wait empty[slot] -> row geometry + one TMA bulk copy per row -> full[slot]
-//                   then (storer role)  wait out_full[g] of tile m - kGroups -> coalesced copy of its features
-//                                       to HBM -> out_empty[g]
-//   worker group g: for its tiles       wait full[slot] -> one channel-window (or one of its two sweeps) per
-//                                       thread, register FFT -> arrive empty[slot]
-//                                       wait out_empty[g] -> staging tile [row][window][band] -> arrive out_full[g]
+//   producer warp p: for its tiles m = p, p + P, ...   wait empty[slot] -> arm full[slot], publish armed[slot],
+//                                                       one TMA bulk copy per row
+//   worker group g : for its tiles m = g, g + G, ...   wait armed[slot], full[slot] -> one sweep of one channel-window
+//                                                       per thread, register FFT -> arrive empty[slot]
+//                                                       group barrier -> staging tile [window][row][band] -> group
+//                                                       barrier -> the group writes its tile to HBM (store_tile)
 //
+// kSplit == 2: even-sweep warps and odd-sweep warps stage their partial band energies; store_tile adds them and does
+//              the epilogue (the same additions as the one-thread form, so the results are bit-identical).
 // kSplit == 1: a worker runs both sweeps and the epilogue and stages (de, psd).
-// kSplit == 2: even-sweep warps and odd-sweep warps stage their partial band energies; the storer adds them
-//              and does the epilogue (the same additions, so the result is bit-identical to kSplit == 1).
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const Job job)
@@ -299,7 +284,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   // and its row -- packed into one word that is re-read from shared memory every tile (the compiler otherwise
   // rematerialises the lane-map look-up, an indexed constant load with ~1 us of latency, twice per tile).
   int* const thread_meta = reinterpret_cast<int*>(out_stage + C::kGroups * 2 * C::kOutFloats);   // [kWorkers]
-  __shared__ uint64_t full_bar[C::kSlots], empty_bar[C::kSlots], out_full_bar[C::kGroups], out_empty_bar[C::kGroups];
+  __shared__ uint64_t full_bar[C::kSlots], empty_bar[C::kSlots];
   // armed[s] = number of tiles whose copies have been ISSUED into slot s.  A parity wait on full[s] only tells
   // "phase k" from "phase k - 2" if the waiter is at most one phase ahead of the barrier; worker groups advance
   // independently, so a group can reach tile m before the slot's previous tile (m - kSlots, another group's unless
@@ -331,66 +316,28 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       mbar_init(&empty_bar[s], C::kGroupWarps);
       armed[s] = 0;
     }
-#pragma unroll
-    for (int g = 0; g < C::kGroups; ++g) {
-      mbar_init(&out_full_bar[g], C::kGroupWarps);
-      mbar_init(&out_empty_bar[g], 1);
-    }
     mbar_fence_init();
   }
   __syncthreads();
 
   if (tid >= C::kWorkers) {
-    // ------------------------------------------------ producer / storer warp ------------------------------------
-    // Two cursors: loads run ahead as far as the ring has free slots; with !kGroupStore finished tiles are also
-    // written out here, in order, whenever their group has staged them.  Neither role ever blocks the other.
+    // ------------------------------------------------ producer warps ----------------------------------------------
     const int producer = (tid - C::kWorkers) / 32;
-    int next_load = producer, next_store = C::kGroupStore ? n_mine : 0;
-    while (next_load < n_mine || next_store < n_mine) {
-      bool progressed = false;
-      if (next_load < n_mine) {
-        const int m = next_load;
-        const int s = m % C::kSlots;
-        bool free_slot;
-        if constexpr (C::kGroupStore) {
-          mbar_wait(&empty_bar[s], ((m / C::kSlots) & 1) ^ 1);      // nothing else to do: block
-          free_slot = true;
-        } else {
-          free_slot = mbar_test(&empty_bar[s], ((m / C::kSlots) & 1) ^ 1);
-        }
-        if (free_slot) {
-          const unsigned row0 = tile_row0(m);
-          const unsigned nrows = tile_nrows(row0);
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
-            st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
-          }
-          __syncwarp();
-          for (unsigned r = lane; r < nrows; r += 32) {
-            const long long off = row_offset(job, row0 + r, C::kWindows, nullptr);
-            bulk_copy_g2s(ring + s * C::kSlotFloats + r * C::kRowStride, job.in + off, C::kRowBytes, &full_bar[s]);
-          }
-          __syncwarp();
-          next_load += C::kProducers;
-          progressed = true;
-        }
+    for (int m = producer; m < n_mine; m += C::kProducers) {
+      const int s = m % C::kSlots;
+      mbar_wait(&empty_bar[s], ((m / C::kSlots) & 1) ^ 1);
+      const unsigned row0 = tile_row0(m);
+      const unsigned nrows = tile_nrows(row0);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
+        st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
       }
-      if constexpr (!C::kGroupStore) {
-        if (next_store < next_load) {
-          const int mo = next_store;
-          const int g = mo % C::kGroups;
-          if (mbar_test(&out_full_bar[g], (mo / C::kGroups) & 1)) {
-            const unsigned row0 = tile_row0(mo);
-            const float* const out_a = out_stage + g * 2 * C::kOutFloats;
-            store_tile<C, 32>(job, out_a, out_a + C::kOutFloats, row0, tile_nrows(row0), lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&out_empty_bar[g]);
-            ++next_store;
-            progressed = true;
-          }
-        }
-        if (!progressed) __nanosleep(64);
+      __syncwarp();
+      for (unsigned r = lane; r < nrows; r += 32) {
+        const long long off = row_offset(job, row0 + r, C::kWindows, nullptr);
+        bulk_copy_g2s(ring + s * C::kSlotFloats + r * C::kRowStride, job.in + off, C::kRowBytes, &full_bar[s]);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------ worker warps ----------------------------------------------
@@ -431,12 +378,8 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       // (Handing the slot back right after the radix-8 stage, two DFT-25 earlier, measured 4 % SLOWER in 1 s mode.)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp no longer reads the input slot
-      if constexpr (C::kGroupStore) {
-        // staging tile is free again once every thread of the group finished storing the previous tile
-        if (j > 0) group_barrier(1 + g, C::kGroupThreads);
-      } else {
-        mbar_wait(&out_empty_bar[g], (j & 1) ^ 1);         // staging tile drained by the storer warp
-      }
+      // staging tile is free again once every thread of the group finished storing the previous tile
+      if (j > 0) group_barrier(1 + g, C::kGroupThreads);
       if (live) {
         const int slot_out = (*reinterpret_cast<volatile int*>(thread_meta + tid) >> 14) & 0x7ff;
 #pragma unroll
@@ -445,14 +388,9 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           if constexpr (C::kSplit == 1) out_b[slot_out + b] = vb[b];
         }
       }
-      if constexpr (C::kGroupStore) {
-        group_barrier(1 + g, C::kGroupThreads);            // all of the group's results are staged
-        if (store_tile<C, C::kGroupThreads>(job, out_a, out_b, row0, nrows, gt) && job.status != nullptr)
-          atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&out_full_bar[g]);
-      }
+      group_barrier(1 + g, C::kGroupThreads);              // all of the group's results are staged
+      if (store_tile<C, C::kGroupThreads>(job, out_a, out_b, row0, nrows, gt) && job.status != nullptr)
+        atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
     }
   }
 }

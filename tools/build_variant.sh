@@ -10,7 +10,7 @@ trap 'rm -rf "$tmp"' EXIT
 if [ "$rev" = WORK ]; then
   cp "$root"/eeg2video_b200/csrc/*.cu "$root"/eeg2video_b200/csrc/*.cuh "$root"/eeg2video_b200/csrc/*.h "$tmp"/
 else
-  for f in eegfe_kernels.cu bandpower.cuh cplx.cuh eegfe_tables.h; do git -C "$root" show "$rev:eeg2video_b200/csrc/$f" > "$tmp/$f"; done
+  for f in $(git -C "$root" ls-tree --name-only "$rev" eeg2video_b200/csrc/ | xargs -n1 basename | grep -E "\.(cu|cuh|h)$"); do git -C "$root" show "$rev:eeg2video_b200/csrc/$f" > "$tmp/$f"; done
 fi
 mkdir -p "$tmp/inc"; 
 if [ "$rev" = WORK ]; then cp "$root/include/eegfe.h" "$tmp/inc/"; else git -C "$root" show "$rev:include/eegfe.h" > "$tmp/inc/eegfe.h"; fi
