@@ -68,7 +68,10 @@ def segment_subject(data, fs=FS):
         arr = np.asarray(data)
         if arr.dtype not in (np.float32, np.float64, np.float16, np.int16):
             raise TypeError(f"unsupported recording dtype {arr.dtype}")
-        dev = torch.from_numpy(np.ascontiguousarray(arr)).to(_io.device())
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:                       # memory maps: torch wants a writable buffer to wrap
+            arr = arr.copy()
+        dev = torch.from_numpy(arr).to(_io.device())
     clips = frontend.segment_clips(dev, fs)
     return clips if like_torch else clips.cpu().numpy()
 

@@ -499,3 +499,27 @@ def test_launches_are_cuda_graph_capturable():
         graph.replay()
         want = ops.de_psd_from_raw(raw, mid)
         assert torch.equal(de, want[0]) and torch.equal(psd, want[1])
+
+
+def test_preprocess_all_equals_the_five_scripts(tmp_path, monkeypatch):
+    """One pass from raw recordings == the reference's chain of scripts, file for file."""
+    from eeg2video_b200 import preprocess_all
+    from eeg2video_b200.EEG_preprocessing import extract_DE_PSD_features_1per1s as s1
+    from eeg2video_b200.EEG_preprocessing import extract_DE_PSD_features_1per2s as s2
+    from eeg2video_b200.EEG_preprocessing import extract_DE_PSD_features_1per500ms as s5
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(19)
+    (tmp_path / "data" / "EEG").mkdir(parents=True)
+    np.save(tmp_path / "data" / "EEG" / "sub4.npy", (30 * rng.standard_normal((7, 3, 104004))).astype(np.float64))
+    assert preprocess_all.main(["--out_root", str(tmp_path / "fused"), "--keep-segments"]) == ["sub4.npy"]
+    seg.segment_all_files()
+    ssw.main()
+    s5.main(["--subs", "4"])
+    s2.main(subjects=(4,))
+    s1.main()
+    chain = tmp_path / "data" / "Preprocessing"
+    for d in ("DE_1per2s", "PSD_1per2s", "DE_1per1s", "PSD_1per1s", "DE_500ms_sw", "PSD_500ms_sw",
+              "Segmented_500ms_sw"):
+        a, b = np.load(tmp_path / "fused" / d / "sub4.npy"), np.load(chain / d / "sub4.npy")
+        assert a.dtype == b.dtype and a.shape == b.shape, d
+        assert np.array_equal(a, b), d
