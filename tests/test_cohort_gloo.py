@@ -24,13 +24,13 @@ def _standin(raw):
     return base * 2.0, base + 1.0
 
 
-def _worker(rank, world, port, n_subjects, result_path):
+def _worker(rank, world, port, n_subjects, result_path, overlap=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         full = torch.arange(n_subjects * 7 * 4 * 32, dtype=torch.float32).reshape(n_subjects, 7, 4, 32)
         lo, hi = cohort.shard_bounds(n_subjects, rank, world)
-        de, psd = cohort.process_cohort(full[lo:hi], n_subjects, chunk_subjects=2, compute=_standin)
+        de, psd = cohort.process_cohort(full[lo:hi], n_subjects, chunk_subjects=2, compute=_standin, overlap=overlap)
         if rank == 0:
             want_de, want_psd = _standin(full)
             ok = torch.equal(de, want_de) and torch.equal(psd, want_psd)
@@ -41,9 +41,9 @@ def _worker(rank, world, port, n_subjects, result_path):
         dist.destroy_process_group()
 
 
-def _run(n_subjects, tmp_path):
-    path = os.path.join(tmp_path, f"res_{n_subjects}.pt")
-    mp.spawn(_worker, args=(2, _free_port(), n_subjects, path), nprocs=2, join=True)
+def _run(n_subjects, tmp_path, overlap=False):
+    path = os.path.join(tmp_path, f"res_{n_subjects}_{int(overlap)}.pt")
+    mp.spawn(_worker, args=(2, _free_port(), n_subjects, path, overlap), nprocs=2, join=True)
     res = torch.load(path)
     assert res["ok"] and res["shape"][0] == n_subjects
 
@@ -54,6 +54,12 @@ def test_even_shards_gather(tmp_path):
 
 def test_ragged_shards_gather(tmp_path):
     _run(5, str(tmp_path))
+
+
+def test_overlapped_chunked_gather(tmp_path):
+    """Chunk i's gather is in flight while chunk i + 1 is computed; same result as the sequential path."""
+    _run(10, str(tmp_path), overlap=True)           # 5 subjects per rank, chunks of 2, 2, 1
+    _run(5, str(tmp_path), overlap=True)            # ragged shards: falls back to the sequential path
 
 
 def test_single_process_is_identity():
