@@ -4,6 +4,7 @@
 # <git-rev>: take eeg2video_b200/csrc/* from that revision; WORK: the working tree.
 set -e
 rev=$1; out=$2; shift 2
+mkdir -p "$(dirname "$out")"
 root=$(cd "$(dirname "$0")/.." && pwd)
 tmp=$(mktemp -d "$root/eeg2video_b200/csrc/_var.XXXXXX")
 trap 'rm -rf "$tmp"' EXIT
