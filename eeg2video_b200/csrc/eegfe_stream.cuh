@@ -126,13 +126,17 @@ __device__ EEGFE_STREAM_DUTY void stream_store_tile(const Job* jobp, const float
 // GLMNet raw branch: half-pass q of a tile writes rows q, q + 7, q + 14 of the tile out again as per-channel normalised
 // clips (x * scale[ch] + shift[ch]), 16 lanes x float4 per row -- spread over all passes instead of one warp per tile
 // (as a last-reader duty it cost 40 %: 25.6 KB copied by a single warp per tile).
+constexpr int kNormTableChannels = 256;     // per-channel scale / shift cached in shared memory up to this many channels
 __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const float* slot, unsigned row0, int nrows, int q,
-                                                       int lane16)
+                                                       int lane16, const float* norm_tab)
 {
   for (int r = q; r < nrows; r += StreamCfg::kHalfPasses) {
     const unsigned grow = row0 + r;
     const unsigned ch = grow % job.n_ch;
-    const float sc = __ldg(job.norm_scale + ch), sh = __ldg(job.norm_shift + ch);
+    // (read from global memory, the two factors cost a long-scoreboard stall per row: 20 % of the kernel's stalls)
+    const bool cached = job.n_ch <= kNormTableChannels;
+    const float sc = cached ? norm_tab[ch] : __ldg(job.norm_scale + ch);
+    const float sh = cached ? norm_tab[kNormTableChannels + ch] : __ldg(job.norm_shift + ch);
     const float4* src = reinterpret_cast<const float4*>(slot + r * StreamCfg::kRowStride);
     float4* dst = reinterpret_cast<float4*>(job.norm_out + (job.norm_row0 + grow) * 400);
     float4 v[7];
@@ -168,6 +172,14 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
   // (the barrier is then in phase k or beyond) makes the parity wait unambiguous.
   __shared__ unsigned armed[C::kSlots];
   __shared__ unsigned next_pass;
+  __shared__ float norm_tab[NORM ? 2 * kNormTableChannels : 2];
+  if constexpr (NORM) {
+    if (job.n_ch <= kNormTableChannels)
+      for (unsigned i = threadIdx.x; i < job.n_ch; i += blockDim.x) {
+        norm_tab[i] = job.norm_scale[i];
+        norm_tab[kNormTableChannels + i] = job.norm_shift[i];
+      }
+  }
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -247,7 +259,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
         if (valid) {
           const unsigned r0 = tile_row0(t);
           stream_store_norm_rows(job, ring + s * C::kSlotFloats, r0, tile_nrows(r0),
-                                 static_cast<int>((2 * pass + (lane >> 4)) - t * C::kHalfPasses), lane & 15);
+                                 static_cast<int>((2 * pass + (lane >> 4)) - t * C::kHalfPasses), lane & 15, norm_tab);
         }
         __syncwarp();
         asm volatile("" : "+r"(pass));
