@@ -32,7 +32,8 @@ namespace eegfe {
 #ifndef EEGFE_STREAM_WARPS
 #define EEGFE_STREAM_WARPS 16
 #endif
-template <int ROWS_, int WINDOWS_, int HOP_, int LOAD_, int STRIDE_, int VEC_, int SLOTS_, bool LANEMAP_>
+template <int ROWS_, int WINDOWS_, int HOP_, int LOAD_, int STRIDE_, int VEC_, int SLOTS_, bool LANEMAP_,
+          int WARPS_ = EEGFE_STREAM_WARPS>
 struct StreamCfgT {
   static constexpr int kRows = ROWS_;          // rows per tile
   static constexpr int kWindows = WINDOWS_;    // analysis windows per row
@@ -43,7 +44,7 @@ struct StreamCfgT {
   static constexpr bool kLaneMap = LANEMAP_;   // unit order inside a tile through c_lane_map_500_r16
   static constexpr int kRowBytes = kLoad * 4;
   static constexpr int kSlots = SLOTS_;
-  static constexpr int kWarps = EEGFE_STREAM_WARPS;
+  static constexpr int kWarps = WARPS_;
   static constexpr int kThreads = kWarps * 32;
   static constexpr int kUnits = kRows * kWindows;          // channel-windows per tile
   static constexpr int kHalfPasses = kUnits / 16;
@@ -60,7 +61,10 @@ using StreamCfg = StreamCfgT<16, 7, 50, 400, 404, 2, 7, true>;
 // pre-cut 500 ms windows (the reference's own call pattern, DE_PSD on a materialised (.., 100) array): 64 rows of 100
 // samples, dense rows (LDS.128 over consecutive rows is conflict-free because 100 / 4 = 25 is odd); a tile of
 // contiguous rows arrives with ONE bulk copy.
-using StreamCfgWin100 = StreamCfgT<64, 1, 0, 100, 100, 4, 7, false>;
+#ifndef EEGFE_WIN100_WARPS
+#define EEGFE_WIN100_WARPS 12   // 168 registers, no spills: 11.9 G cw/s against 10.5 G with 16 warps at 128 registers
+#endif
+using StreamCfgWin100 = StreamCfgT<64, 1, 0, 100, 100, 4, 7, false, EEGFE_WIN100_WARPS>;
 
 __constant__ unsigned char c_lane_map_500_r16[112] = {EEGFE_LANE_MAP_500_R16};
 
