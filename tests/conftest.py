@@ -84,7 +84,8 @@ def hostemu():
         e = np.zeros((x.shape[0], 5), dtype=np.float32)
         rc = dll.hostemu_band_energy(x.ctypes.data, x.shape[0], x.shape[1], e.ctypes.data)
         assert rc == 0
-        psd = e / np.array([4, 5, 7, 18, 69], dtype=np.float32)
+        # the device epilogue multiplies by the float32 reciprocal of the bin count (inv_count() in eegfe_kernels.cu)
+        psd = e * (np.float32(1.0) / np.array([4, 5, 7, 18, 69], dtype=np.float32))
         with np.errstate(divide="ignore"):
             de = np.log2(np.float32(100.0) * psd.astype(np.float32)).astype(np.float64)
         return de, psd.astype(np.float64)

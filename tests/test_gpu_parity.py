@@ -523,3 +523,15 @@ def test_preprocess_all_equals_the_five_scripts(tmp_path, monkeypatch):
         a, b = np.load(tmp_path / "fused" / d / "sub4.npy"), np.load(chain / d / "sub4.npy")
         assert a.dtype == b.dtype and a.shape == b.shape, d
         assert np.array_equal(a, b), d
+
+
+@pytest.mark.parametrize("length", (100, 200, 400))
+def test_device_arithmetic_is_bit_identical_to_the_host_emulation(hostemu, length):
+    """tests/hostemu compiles bandpower.cuh for the host with the scalar backend of cplx.cuh; the device runs the packed
+    f32x2 backend.  Same operations in the same order with IEEE round-to-nearest -> the PSD values must agree bit for
+    bit, which is what makes the CPU tier's error figures the GPU's."""
+    rng = np.random.default_rng(length + 1)
+    x = (30 * rng.standard_normal((4096, length)) + rng.uniform(-50, 50, (4096, 1))).astype(np.float32)
+    _, psd_emu = hostemu(x)                                           # float64 view of float32 values
+    de, psd = frontend.de_psd_windows(torch.from_numpy(x).to(DEV))
+    assert np.array_equal(psd.cpu().numpy(), psd_emu.astype(np.float32))
