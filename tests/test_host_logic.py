@@ -111,3 +111,42 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1 and sizes == cohort.shard_sizes(n, world)
+
+
+def test_convert_directory_is_the_scripts_file_loop(tmp_path):
+    """The shared directory helper behind every script entry point, with a stand-in conversion (no GPU)."""
+    import numpy as np
+    from eeg2video_b200.EEG_preprocessing import _io
+    src = tmp_path / "in"
+    src.mkdir()
+    for n, shape in ((1, (2, 3)), (2, (2, 3)), (10, (4,))):
+        np.save(src / f"sub{n}.npy", np.full(shape, n, dtype=np.float32))
+    (src / "notes.txt").write_text("ignored")
+    logs = []
+    done = _io.convert_directory(str(src), (str(tmp_path / "a"), str(tmp_path / "b")), lambda x: (x + 1, x * 2),
+                                 accept=lambda x: None if x.ndim == 2 else f"unexpected shape {x.shape}", log=logs.append)
+    assert done == ["sub1.npy", "sub2.npy"]                       # sorted, .npy only, the 1-D file vetoed
+    assert any("Skipping sub10.npy: unexpected shape (4,)" in line for line in logs)
+    assert np.array_equal(np.load(tmp_path / "a" / "sub2.npy"), np.full((2, 3), 3, np.float32))
+    assert np.array_equal(np.load(tmp_path / "b" / "sub1.npy"), np.full((2, 3), 2, np.float32))
+    only = _io.convert_directory(str(src), (str(tmp_path / "c"),), lambda x: x, names=["sub2.npy"], log=logs.append)
+    assert only == ["sub2.npy"] and not (tmp_path / "c" / "sub1.npy").exists()
+    with pytest.raises(FileNotFoundError):
+        _io.convert_directory(str(src), (str(tmp_path / "d"),), lambda x: x, names=["sub99.npy"], log=logs.append)
+
+
+def test_clip_start_matches_the_reference_formula():
+    from eeg2video_b200.EEG_preprocessing import segment_raw_signals_200Hz as seg
+    for fs in (200, 250, 1000):
+        for c in (0, 1, 39):
+            for r in (0, 4):
+                assert seg.clip_start(c, r, fs) == c * (3 * fs + 5 * 2 * fs) + 3 * fs + r * 2 * fs   # :58-64
+    assert seg.clip_start(39, 4) + 400 == 104000
+
+
+def test_preprocess_all_cli_parses_like_the_scripts():
+    from eeg2video_b200 import preprocess_all
+    assert set(preprocess_all.FEATURE_DIRS) == {"2s", "1s", "500ms"}
+    assert preprocess_all.FEATURE_DIRS["1s"][2].__name__ == "float64"      # the 1 s files are float64 in the reference
+    with pytest.raises(SystemExit):
+        preprocess_all.main(["--no-such-flag"])
