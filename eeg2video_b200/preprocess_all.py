@@ -11,6 +11,11 @@ under ``out_root`` with the reference's file names, shapes and dtypes (float32; 
 every downstream consumer reads the same files.  The intermediate clip / window tensors are never built unless asked for.
 
     python -m eeg2video_b200.preprocess_all --eeg_root ./data/EEG --out_root ./data/Preprocessing [--subs 1 2 3]
+
+Several GPUs: subjects are independent, so there is nothing to exchange -- launch one process per GPU and every rank
+takes every WORLD_SIZE-th recording on its own device (no process group is created):
+
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 -m eeg2video_b200.preprocess_all ...
 """
 import argparse
 import os
@@ -38,10 +43,23 @@ def process_recording(raw, modes=("2s", "1s", "500ms")):
     return out, dev
 
 
+def shard_for_this_rank(names, env=None):
+    """The recordings this process handles when launched by torchrun (RANK / WORLD_SIZE in the environment):
+    names[rank::world]; all of them when run alone."""
+    env = os.environ if env is None else env
+    world, rank = int(env.get("WORLD_SIZE", "1")), int(env.get("RANK", "0"))
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad RANK / WORLD_SIZE: {rank} / {world}")
+    return list(names)[rank::world]
+
+
 def preprocess_all(eeg_root="./data/EEG", out_root="./data/Preprocessing", subs=None, keep_segments=False, log=print):
-    """Returns the list of file names written."""
+    """Returns the list of file names written (by this rank)."""
     names = sorted(n for n in os.listdir(eeg_root) if n.endswith(".npy")) if subs is None \
         else [f"sub{int(s)}.npy" for s in subs]
+    names = shard_for_this_rank(names)
+    if torch.cuda.is_available() and "LOCAL_RANK" in os.environ:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
     done = []
     for name in names:
         recording = np.load(os.path.join(eeg_root, name), mmap_mode="r")

@@ -150,3 +150,13 @@ def test_preprocess_all_cli_parses_like_the_scripts():
     assert preprocess_all.FEATURE_DIRS["1s"][2].__name__ == "float64"      # the 1 s files are float64 in the reference
     with pytest.raises(SystemExit):
         preprocess_all.main(["--no-such-flag"])
+
+
+def test_preprocess_all_shards_recordings_by_rank():
+    from eeg2video_b200 import preprocess_all
+    names = [f"sub{i}.npy" for i in range(1, 11)]
+    parts = [preprocess_all.shard_for_this_rank(names, {"WORLD_SIZE": "4", "RANK": str(r)}) for r in range(4)]
+    assert sorted(sum(parts, [])) == sorted(names) and [len(p) for p in parts] == [3, 3, 2, 2]
+    assert preprocess_all.shard_for_this_rank(names, {}) == names
+    with pytest.raises(ValueError):
+        preprocess_all.shard_for_this_rank(names, {"WORLD_SIZE": "2", "RANK": "2"})
