@@ -1,13 +1,20 @@
 // libeegfe.so -- fused segmentation + Hann + 200-point FFT + five-band DE/PSD for B200 (sm_100a).
 //
-// One persistent kernel per analysis mode.  A CTA owns a tile of R rows (one row = one channel of one 2 s clip,
-// or one pre-cut window); warp 0 pulls the rows of the NEXT tile from HBM into shared memory with one 1-D TMA
-// bulk copy per row (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) while all warps work on the current
-// tile.  Rows are addressed by index arithmetic on the raw recording (clip (c, r) of a block starts at sample
-// c*2600 + 600 + r*400; window w at +50 w), so neither the clip tensor nor the sliding-window tensor of the
-// reference is ever materialised.  Each thread then owns one channel-window: it reads its samples from shared
-// memory (LDS.64), runs the register-resident prime-factor FFT of bandpower.cuh with packed f32x2 arithmetic and
-// writes 5 PSD + 5 DE values.  No tensor cores (FFT + reduction, no dense contraction), no inter-CTA traffic.
+// Persistent kernels, one CTA per SM.  Rows (one row = one channel of one 2 s clip, or one pre-cut window) are
+// addressed by index arithmetic on the raw recording (clip (c, r) of a block starts at sample c*2600 + 600 + r*400;
+// window w at +50 w) and pulled into a ring of shared-memory slots with 1-D TMA bulk copies (cp.async.bulk ...
+// mbarrier::complete_tx, SASS UBLKCP), so neither the clip tensor nor the sliding-window tensor of the reference is
+// ever materialised.  One thread owns one channel-window (or one of its two sweeps): it reads its samples from shared
+// memory, runs the register-resident prime-factor FFT of bandpower.cuh in packed f32x2 arithmetic and contributes 5 PSD
+// + 5 DE values to a staged tile that leaves as linear, coalesced stores.  No tensor cores (FFT + reduction, no dense
+// contraction), no inter-CTA traffic.
+//
+//   eegfe_stream.cuh   de_psd_stream_kernel   500 ms windows (sliding over clip rows, or pre-cut): FP32-pipe-bound;
+//                                             16 identical warps draw passes from a counter, tile duties fall to the
+//                                             last finisher
+//   this file          de_psd_kernel          1 s / 2 s windows: HBM-bound; producer warps + worker groups on a ring
+//                      de_psd_kernel_unaligned  rows that are only 4-byte aligned (no TMA): cooperative loads
+//                      gather / sliding-window / statistics kernels for the materialising and "next row" entry points
 //
 // C ABI: include/eegfe.h.  Reference semantics: see the citations in that header and in bandpower.cuh.
 #include <cuda_runtime.h>
