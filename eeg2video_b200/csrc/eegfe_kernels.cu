@@ -90,8 +90,8 @@ struct Cfg {
 // (-DEEGFE_NOCOMPUTE) reaches 94 % of the measured HBM peak there, with four worker groups the full kernel 83 %.
 // Seven groups (14 worker + 2 producer warps = 16 warps at 128 registers, no spills in the split-sweep form) keep the
 // FP32 pipe fed while other groups wait at their store barriers: 5 groups 87 %, 6 groups 97 %, 7 groups 100 % of the
-// (copy-measured) HBM peak.  The 2 s kernel is bounded by its access pattern instead -- 800 B out of every 1600 B, which
-// L2 rounds up to 896 B of 128-byte lines: 83 % with or without the FFT -- and keeps four groups.
+// (copy-measured) HBM peak.  The 2 s kernel is bounded by the memory side instead -- 800-byte requests, 83 % with or
+// without the FFT (dense 800-byte rows of pre-cut windows reach 85 % the same way) -- and keeps four groups.
 // Ring sizing: these kernels are HBM-bound at 800 B (400 B) per channel-window and want ~100 KB per SM in flight, hence
 // small tiles and as many surplus slots as shared memory holds; a tile is due every ~1 us per SM, so each group writes
 // its own tile and the producers only issue copies.  One bulk copy per row costs a producer warp ~30 issue cycles
