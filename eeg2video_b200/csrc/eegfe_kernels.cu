@@ -78,6 +78,9 @@ struct Cfg {
   static_assert(kRowBytes % 16 == 0 && kRowStride % 4 == 0, "TMA bulk copies need 16-byte aligned rows");
   static_assert(SPLIT_ == 1 || SPLIT_ == 2, "one or two threads per channel-window");
   static_assert(GROUPS_ <= 15, "one named barrier per group");
+  // every slot must be refilled by ONE producer warp, in order: with tiles of a slot spread over several producers
+  // one of them can wait on the slot's empty barrier two phases ahead, where the parity test reads "free"
+  static_assert(SLOTS_ % PRODUCERS_ == 0, "producer p owns the slots congruent to p modulo kProducers");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
 // Shared-memory bank rules behind PAD / VEC (B200: 32 banks x 4 B; 64-bit loads are served per half-warp,
@@ -91,7 +94,8 @@ struct Cfg {
 // Seven groups (14 worker + 2 producer warps = 16 warps at 128 registers, no spills in the split-sweep form) keep the
 // FP32 pipe fed while other groups wait at their store barriers: 5 groups 87 %, 6 groups 97 %, 7 groups 100 % of the
 // (copy-measured) HBM peak.  The 2 s kernel is bounded by the memory side instead -- 800-byte requests, 83 % with or
-// without the FFT (dense 800-byte rows of pre-cut windows reach 85 % the same way) -- and keeps four groups.
+// without the FFT with two producer warps: it was the ISSUE rate of its 800-byte bulk copies (~30 issue cycles each on a
+// producer warp).  Four producer warps: 89 %; more groups do not help (they spill at 128 registers).
 // Ring sizing: these kernels are HBM-bound at 800 B (400 B) per channel-window and want ~100 KB per SM in flight, hence
 // small tiles and as many surplus slots as shared memory holds; a tile is due every ~1 us per SM, so each group writes
 // its own tile and the producers only issue copies.  One bulk copy per row costs a producer warp ~30 issue cycles
@@ -101,7 +105,7 @@ struct Cfg {
 //                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP PROD
 using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, 1>;
 using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 7, 8, 1, 4, 4, 2, false, 2>;  // 7 x 64 + 64 thr, 218 KB
-using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, 2>;    // 4 x 64 + 64 (samples 0..199)
+using CfgTwoSec     = Cfg<200, 1, 0, 8, kHannTwoSec, 32, 4, 8, 1, 4, 4, 2, false, 4>;    // 4 x 64 + 128 (samples 0..199)
 using CfgWin100     = Cfg<100, 1, 0, 4, kHannHalfSec, 64, 4, 8, 1, 0, 4, 1, false, 2>;
 using CfgWin200     = Cfg<200, 1, 0, 8, kHannOneSec, 32, 7, 8, 1, 4, 4, 2, false, 2>;    // 7 x 64 + 64, pre-cut 1 s
 
