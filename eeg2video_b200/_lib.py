@@ -35,6 +35,7 @@ SIGNATURES = {
     "eegfe_launch_geometry": (_int, [_int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
                                      ctypes.POINTER(_int)]),
     "eegfe_launch_count": (_i64, []),
+    "eegfe_tma_launch_count": (_i64, []),
 }
 
 _lib = None
@@ -77,6 +78,10 @@ def check(code):
 
 def launch_count():
     return int(load().eegfe_launch_count())
+
+
+def tma_launch_count():
+    return int(load().eegfe_tma_launch_count())
 
 
 def launch_geometry(mode):

@@ -19,6 +19,9 @@
 // C ABI: include/eegfe.h.  Reference semantics: see the citations in that header and in bandpower.cuh.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "../../include/eegfe.h"
 #include "bandpower.cuh"
@@ -40,6 +43,7 @@ struct Job {
   long long ch_stride;    // elements between channel rows of one unit
   unsigned d1, d2;
   unsigned n_ch;
+  long long t_extent;     // valid elements of a channel row (tensor-map bound of the time axis); 0 = unknown
   // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = x * scale[ch] + shift[ch]
   float* norm_out;
   const float* norm_scale;
@@ -159,8 +163,8 @@ __device__ __forceinline__ long long row_offset(const Job& job, unsigned g, int 
   const unsigned c = rem / job.d2;
   const unsigned r = rem - c * job.d2;
   if (out_base) *out_base = static_cast<int>((u * n_windows * job.n_ch + ch) * 5u);
-  return job.base + static_cast<long long>(q) * job.s0 + static_cast<int>(c) * job.s1 + static_cast<int>(r) * job.s2 +
-         static_cast<long long>(ch) * job.ch_stride;
+  return job.base + static_cast<long long>(q) * job.s0 + static_cast<long long>(c) * job.s1 +
+         static_cast<long long>(r) * job.s2 + static_cast<long long>(ch) * job.ch_stride;
 }
 
 // E_b -> psd_b = E_b / count_b (DE_PSD.py:66), de_b = log2(100 psd_b) (:68); counts 4, 5, 7, 18, 69.
@@ -265,6 +269,7 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
 
 }  // namespace eegfe
 #include "eegfe_stream.cuh"
+#include "eegfe_tma.cuh"
 namespace eegfe {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -593,17 +598,42 @@ __global__ void channel_stats_finish_kernel(const double* __restrict__ partial, 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_tma_launches{0};
+
+// ---- per-device state: one process may drive several GPUs (cudaFuncSetAttribute and the SM count are per device) ----
+constexpr int kMaxDevices = 64;
+
+static int device_ordinal()
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
 
 static int sm_count()
 {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = device_ordinal();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+
+// Opt one kernel in to `bytes` of dynamic shared memory on the current device, once per (kernel, device).
+// `mask` is the kernel's own bit set of devices already configured (racing threads both set the attribute: harmless).
+template <class K>
+static int configure_smem(std::atomic<unsigned long long>& mask, K kernel, int bytes)
+{
+  const unsigned long long bit = 1ull << device_ordinal();
+  if (mask.load(std::memory_order_acquire) & bit) return 0;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  mask.fetch_or(bit, std::memory_order_release);
+  return 0;
 }
 
 // 500 ms mode, 16-byte aligned rows: the streaming kernel (eegfe_stream.cuh), one CTA of 16 warps per SM.
@@ -615,25 +645,119 @@ static int launch_stream(const Job& job, cudaStream_t stream)
   unsigned grid = static_cast<unsigned>(sm_count());
   if (grid > n_tiles) grid = n_tiles;
   constexpr bool kCanNorm = SC::kLoad == 400 && SC::kWindows == 7;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(de_psd_stream_kernel<SC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SC::kSmemBytes);
-    if constexpr (kCanNorm) {
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(de_psd_stream_kernel<SC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SC::kSmemBytes);
-    }
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0}, configured_norm{0};
   if (job.norm_out != nullptr) {
-    if constexpr (kCanNorm) de_psd_stream_kernel<SC, true><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
-    else return EEGFE_EINVAL;
+    if constexpr (kCanNorm) {
+      const int rc = configure_smem(configured_norm, de_psd_stream_kernel<SC, true>, SC::kSmemBytes);
+      if (rc != 0) return rc;
+      de_psd_stream_kernel<SC, true><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
+    } else {
+      return EEGFE_EINVAL;
+    }
   } else {
+    const int rc = configure_smem(configured, de_psd_stream_kernel<SC, false>, SC::kSmemBytes);
+    if (rc != 0) return rc;
     de_psd_stream_kernel<SC, false><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
   }
   ++g_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---- window-box kernel (eegfe_tma.cuh): tensor map over the recording, one TMA tensor copy per tile ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+  // libcuda is not linked: the entry point comes from the runtime (nullptr on a driver without tensor maps)
+  static const EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static bool legacy_forced()
+{
+#ifdef EEGFE_FORCE_LEGACY
+  return true;
+#endif
+  static const bool v = [] { const char* e = getenv("EEGFE_LEGACY_KERNELS"); return e != nullptr && e[0] == '1'; }();
+  return v;
+}
+
+constexpr int kTmaNotApplicable = -1000;     // internal: the caller falls back to the 1-D bulk-copy kernels
+
+// Returns kTmaNotApplicable when this job cannot use the window-box kernel (shape, alignment, driver).
+template <class TC>
+static int launch_tma(const Job& job, cudaStream_t stream)
+{
+  if (job.total_rows == 0) return 0;
+  if (legacy_forced() || job.norm_out != nullptr) return kTmaNotApplicable;
+  const EncodeTiledFn encode = encode_tiled_fn();
+  if (encode == nullptr) return kTmaNotApplicable;
+  const bool rows_mode = (job.n_ch == 1 && job.d1 == 1 && job.ch_stride == 0 && TC::kWindows == 1);
+  TmaJob tj{};
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t box[3], estride[3] = {1, 1, 1};
+  if (rows_mode) {
+    if (job.s0 < TC::kLoad || job.base != 0) return kTmaNotApplicable;
+    tj.rows_per_tile = TC::kMaxRows;
+    tj.n_units = job.total_rows;
+    tj.n_groups = (job.total_rows + TC::kMaxRows - 1) / TC::kMaxRows;
+    gdim[0] = TC::kLoad;
+    gdim[1] = job.total_rows;
+    gdim[2] = 1;
+    gstride[0] = static_cast<cuuint64_t>(job.s0) * 4;
+    gstride[1] = gstride[0] * job.total_rows;
+  } else {
+    if (job.n_ch < 16 || job.n_ch > TC::kMaxRows || job.t_extent <= 0 || job.base < 0) return kTmaNotApplicable;
+    const unsigned n_clips = job.total_rows / job.n_ch;
+    const unsigned n_blocks = (n_clips + job.d1 - 1) / job.d1;
+    tj.rows_per_tile = job.n_ch;
+    tj.n_groups = n_clips;
+    tj.n_units = static_cast<unsigned long long>(n_clips) * TC::kWindows * job.n_ch;
+    gdim[0] = static_cast<cuuint64_t>(job.t_extent);
+    gdim[1] = job.n_ch;
+    gdim[2] = n_blocks;
+    gstride[0] = static_cast<cuuint64_t>(job.ch_stride) * 4;
+    gstride[1] = (n_blocks > 1 && job.s0 > 0) ? static_cast<cuuint64_t>(job.s0) * 4 : gstride[0] * job.n_ch;
+  }
+  if (gstride[0] % 16 != 0 || gstride[1] % 16 != 0 || gstride[0] >= (1ull << 40) || gstride[1] >= (1ull << 40) ||
+      gdim[0] > (1ull << 32) || gdim[1] > (1ull << 32) || gdim[2] > (1ull << 32))
+    return kTmaNotApplicable;
+  box[0] = TC::kLoad;
+  box[1] = tj.rows_per_tile;
+  box[2] = 1;
+#ifndef EEGFE_TMA_L2_PROMOTION
+#define EEGFE_TMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
+  if (encode(&tj.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(job.in), gdim, gstride, box, estride,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, EEGFE_TMA_L2_PROMOTION,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return kTmaNotApplicable;
+  tj.de = job.de;
+  tj.psd = job.psd;
+  tj.status = job.status;
+  tj.base = static_cast<int>(job.base);
+  tj.s1 = job.s1;
+  tj.s2 = job.s2;
+  tj.d1 = job.d1;
+  tj.d2 = job.d2;
+  tj.rows_mode = rows_mode ? 1 : 0;
+  const int smem = TC::smem_bytes(static_cast<int>(tj.rows_per_tile));
+  static std::atomic<unsigned long long> configured{0};
+  const int rc = configure_smem(configured, de_psd_tma_kernel<TC>, TC::smem_bytes(TC::kMaxRows));
+  if (rc != 0) return rc;
+  unsigned grid = static_cast<unsigned>(sm_count());
+  if (grid > tj.n_groups) grid = tj.n_groups;
+  de_psd_tma_kernel<TC><<<grid, TC::kThreads, smem, stream>>>(tj);
+  ++g_launches;
+  ++g_tma_launches;
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -645,30 +769,30 @@ static int launch(const Job& job, bool aligned16, cudaStream_t stream)
   const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (aligned16) {
     if constexpr (C::kLoad == 400 && C::kWindows == 7) {
-      return launch_stream<StreamCfg>(job, stream);        // 500 ms sliding windows: the streaming kernel
+      // 500 ms sliding windows: the window-box kernel, else (few / many channels, GLMNet product) the streaming kernel
+      const int rc = launch_tma<TmaCfg500>(job, stream);
+      if (rc != kTmaNotApplicable) return rc;
+      return launch_stream<StreamCfg>(job, stream);
     } else if constexpr (C::kLoad == 100 && C::kWindows == 1) {
-      return launch_stream<StreamCfgWin100>(job, stream);  // pre-cut 500 ms windows: the streaming kernel, dense rows
+      // pre-cut 500 ms windows: dense rows
+      const int rc = launch_tma<TmaCfgWin100>(job, stream);
+      if (rc != kTmaNotApplicable) return rc;
+      return launch_stream<StreamCfgWin100>(job, stream);
     } else {
       if (job.norm_out != nullptr) return EEGFE_EINVAL;
       unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
       if (grid > n_tiles) grid = n_tiles;
-      static bool configured = false;
-      if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(de_psd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        configured = true;
-      }
+      static std::atomic<unsigned long long> configured{0};
+      const int rc = configure_smem(configured, de_psd_kernel<C>, C::kSmemBytes);
+      if (rc != 0) return rc;
       de_psd_kernel<C><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
     }
   } else {
     if (job.norm_out != nullptr) return EEGFE_EINVAL;     // the normalised-clip product needs 16-byte aligned rows
-    static bool configured = false;
+    static std::atomic<unsigned long long> configured{0};
     const int smem = C::kSlotFloats * 4 * kUnalignedTiles<C>;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(de_psd_kernel_unaligned<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      configured = true;
-    }
+    const int rc = configure_smem(configured, de_psd_kernel_unaligned<C>, smem);
+    if (rc != 0) return rc;
     unsigned grid = static_cast<unsigned>(sm_count()) * (smem <= 110 * 1024 ? 2 : 1);
     const unsigned n_groups = (n_tiles + kUnalignedTiles<C> - 1) / kUnalignedTiles<C>;
     if (grid > n_groups) grid = n_groups;
@@ -794,6 +918,7 @@ int eegfe_de_psd_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t 
   job.de = de;
   job.psd = psd;
   job.status = status;
+  job.t_extent = block_len;
   return dispatch_clip_mode(mode, job, n_blocks * 200, 200, block_stride,
                             is_aligned16(raw, {block_stride, ch_stride}, 4), static_cast<cudaStream_t>(stream));
 }
@@ -810,6 +935,7 @@ int eegfe_de_psd_from_concepts(const float* x, int64_t n_blocks, int n_ch, int64
   Job job = raw_geometry(n_ch, block_stride, ch_stride);
   job.base = first_offset;
   job.s1 = static_cast<int>(concept_stride);
+  job.t_extent = ch_stride;
   job.in = x;
   job.de = de;
   job.psd = psd;
@@ -887,6 +1013,7 @@ int eegfe_de_psd_from_clips(const float* clips, int64_t n_clips, int n_ch, int m
   job.d1 = 1;
   job.d2 = 1;
   job.ch_stride = 400;
+  job.t_extent = 400;
   job.n_ch = static_cast<unsigned>(n_ch);
   return dispatch_clip_mode(mode, job, n_clips, 1, job.s0, is_aligned16(clips, {}, 4),
                             static_cast<cudaStream_t>(stream));
@@ -1059,6 +1186,8 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
   return 0;
 }
 
-int64_t eegfe_launch_count(void) { return g_launches; }
+int64_t eegfe_launch_count(void) { return g_launches.load(); }
+
+int64_t eegfe_tma_launch_count(void) { return g_tma_launches.load(); }
 
 }  // extern "C"

@@ -192,6 +192,11 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 /* Number of kernels this library has launched since load (gpu_launches accounting in bench.py). */
 int64_t eegfe_launch_count(void);
 
+/* Of those, launches of the window-box kernels (one TMA tensor copy per tile, csrc/eegfe_tma.cuh).  Tests use it to
+ * tell that the fast path, not the 1-D bulk-copy fallback, served a call.  Setting EEGFE_LEGACY_KERNELS=1 in the
+ * environment before the first call keeps every job on the fallback kernels (A/B measurements). */
+int64_t eegfe_tma_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

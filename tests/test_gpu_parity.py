@@ -302,6 +302,47 @@ def test_streaming_kernel_many_tiles_per_cta():
     assert torch.equal(a[0][3], de_w) and torch.equal(a[1][3], psd_w)
 
 
+def test_window_box_kernel_serves_the_standard_shapes(subject):
+    """The 500 ms jobs of the reference's shapes (16..64 channels, 16-byte aligned rows) run on the window-box kernel
+    (one TMA tensor copy per tile, csrc/eegfe_tma.cuh); other channel counts run on the 1-D bulk-copy kernel.  Both
+    use the same arithmetic core, so they must agree bit for bit, channel for channel."""
+    raw, _ = subject
+    before = _lib.tma_launch_count()
+    de, psd = frontend.de_psd_from_raw(raw[:2], "500ms")
+    assert _lib.tma_launch_count() == before + 1
+    wide = torch.cat([raw[:2], raw[:2, :10]], dim=1).contiguous()                   # 72 channels -> fallback kernel
+    before = _lib.tma_launch_count()
+    de_w, psd_w = frontend.de_psd_from_raw(wide, "500ms")
+    assert _lib.tma_launch_count() == before
+    assert torch.equal(de_w[..., :62, :], de) and torch.equal(psd_w[..., :62, :], psd)
+    assert torch.equal(de_w[..., 62:, :], de[..., :10, :])
+    # pre-cut windows: dense rows -> window-box kernel, strided rows whose pitch is not a multiple of 16 bytes -> fallback
+    wins = frontend.sliding_windows(frontend.segment_clips(raw[:1])).reshape(-1, 100)
+    before = _lib.tma_launch_count()
+    a = ops.de_psd_windows(wins)
+    assert _lib.tma_launch_count() == before + 1
+    padded = torch.empty((wins.shape[0], 102), device=DEV)
+    padded[:, :100] = wins
+    b = ops.de_psd_windows(padded[:, :100])
+    assert _lib.tma_launch_count() == before + 1
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[0].reshape(de[0].shape), de[0])
+
+
+@pytest.mark.parametrize("n_clips,n_ch", ((1, 16), (147, 20), (149, 33), (300, 48), (1000, 62), (2077, 64), (31, 63)))
+def test_window_box_kernel_ragged(n_clips, n_ch):
+    """Window-box kernel: fewer clips than SMs, clip counts that do not divide by the grid, passes that straddle
+    two or three tiles (n_ch < 32), slot recycling (many tiles per CTA) -- against the float64 closed form."""
+    rng = np.random.default_rng(77 * n_clips + n_ch)
+    clips = (30 * rng.standard_normal((n_clips, n_ch, 400)) + rng.uniform(-50, 50, (n_clips, n_ch, 1))).astype(np.float32)
+    before = _lib.tma_launch_count()
+    de, psd = frontend.de_psd_from_clips(torch.from_numpy(clips).to(DEV), "500ms")
+    assert _lib.tma_launch_count() == before + 1
+    wins = np.stack([clips[..., 50 * w:50 * w + 100] for w in range(7)], axis=1)
+    de_ref, psd_ref = oracle.de_psd_closed_form(wins, 200, 0.5)
+    assert_features_close(de.cpu().numpy(), psd.cpu().numpy(), de_ref, psd_ref)
+
+
 def test_unaligned_block_length_uses_fallback_loader():
     """T = 104001: rows are only 4-byte aligned, so TMA bulk copies are impossible; same results required."""
     raw = synth.synth_blocks(1, 5, device=DEV, channels=62, block_len=104001)
