@@ -705,11 +705,11 @@ static int launch_tma(const Job& job, cudaStream_t stream)
   cuuint64_t gdim[3], gstride[2];
   cuuint32_t box[3], estride[3] = {1, 1, 1};
   if (rows_mode) {
-    if (job.s0 < TC::kLoad || job.base != 0) return kTmaNotApplicable;
+    if (job.s0 < TC::kWin || job.base != 0) return kTmaNotApplicable;
     tj.rows_per_tile = TC::kMaxRows;
     tj.n_units = job.total_rows;
     tj.n_groups = (job.total_rows + TC::kMaxRows - 1) / TC::kMaxRows;
-    gdim[0] = TC::kLoad;
+    gdim[0] = TC::kWin;                      // samples past the window are out of bounds: zero-filled, never read
     gdim[1] = job.total_rows;
     gdim[2] = 1;
     gstride[0] = static_cast<cuuint64_t>(job.s0) * 4;
@@ -749,6 +749,9 @@ static int launch_tma(const Job& job, cudaStream_t stream)
   tj.d1 = job.d1;
   tj.d2 = job.d2;
   tj.rows_mode = rows_mode ? 1 : 0;
+  tj.in = job.in;
+  tj.block_stride = job.s0;
+  tj.ch_stride = job.ch_stride;
   const int smem = TC::smem_bytes(static_cast<int>(tj.rows_per_tile));
   static std::atomic<unsigned long long> configured{0};
   const int rc = configure_smem(configured, de_psd_tma_kernel<TC>, TC::smem_bytes(TC::kMaxRows));
@@ -780,6 +783,16 @@ static int launch(const Job& job, bool aligned16, cudaStream_t stream)
       return launch_stream<StreamCfgWin100>(job, stream);
     } else {
       if (job.norm_out != nullptr) return EEGFE_EINVAL;
+#ifndef EEGFE_RING_1S_2S
+      {
+        // 200-sample windows start on 16-byte boundaries: window-box kernel (one TMA tensor copy per tile)
+        int rc = kTmaNotApplicable;
+        if constexpr (C::kWindows == 2) rc = launch_tma<TmaCfgOneSec>(job, stream);
+        else if constexpr (C::kHann == kHannTwoSec) rc = launch_tma<TmaCfgTwoSec>(job, stream);
+        else rc = launch_tma<TmaCfgWin200>(job, stream);
+        if (rc != kTmaNotApplicable) return rc;
+      }
+#endif
       unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
       if (grid > n_tiles) grid = n_tiles;
       static std::atomic<unsigned long long> configured{0};

@@ -4,8 +4,10 @@
 // is never written to HBM -- but it IS what shared memory holds here: a tile is the box [n_ch rows][LOAD samples]
 // that `cp.async.bulk.tensor` (SASS UTMALDG) cuts out of the raw recording at the element coordinate
 //     (c * 2600 + 600 + r * 400 + HOP * w,  channel 0,  block)          (segment_raw_signals_200Hz.py:58-65)
-// A tensor-map copy may start at ANY element, so every window -- also the odd ones, which sit 8 bytes off a
-// 16-byte boundary in the recording -- lands 128-byte aligned with dense 400-byte rows:
+// Every window lands 128-byte aligned with dense 400-byte rows.  A tiled tensor copy must start on a 16-byte
+// boundary of the innermost axis (measured: x = 2 floats raises "illegal instruction", tools/microbench/tma_align.cu),
+// which the even windows do (x = 0, 100, 200, 300 floats into a clip); the odd ones (x = 50, 150, 250) sit 8 bytes
+// off and are fetched by the refilling warp with 8-byte cp.async (LDGSTS.64) instead -- same mbarrier, same layout:
 //   * LDS.128 with lanes over consecutive rows is conflict-free (row stride / 16 B = 25 is odd); no lane map;
 //   * the 50 % overlap of neighbouring windows is served by L2 (the seven boxes of a clip are fetched back to back
 //     by the same CTA), so DRAM still sees 1600 B per channel-clip while shared memory receives 2800 B;
@@ -39,9 +41,10 @@ namespace eegfe {
 #define EEGFE_TMA_SLOTS 8
 #endif
 
-template <int LOAD_, int WINDOWS_, int HOP_, int NI_, int HANN_, int SLOTS_, int WARPS_>
+template <int LOAD_, int WIN_, int WINDOWS_, int HOP_, int NI_, int HANN_, int SLOTS_, int WARPS_, int MAXROWS_>
 struct TmaCfgT {
   static constexpr int kLoad = LOAD_;          // samples per row of a box (= floats between rows in shared memory)
+  static constexpr int kWin = WIN_;            // samples of a window that are read (kLoad - kWin = bank-skew padding)
   static constexpr int kWindows = WINDOWS_;    // boxes per clip
   static constexpr int kHop = HOP_;
   static constexpr int kNi = NI_;
@@ -49,7 +52,7 @@ struct TmaCfgT {
   static constexpr int kSlots = SLOTS_;
   static constexpr int kWarps = WARPS_;
   static constexpr int kThreads = WARPS_ * 32;
-  static constexpr int kMaxRows = 64;          // rows per tile the ring is dimensioned for
+  static constexpr int kMaxRows = MAXROWS_;    // rows per tile the ring is dimensioned for
   static constexpr int kScratchFloats = 2 * 160;   // per warp: 32 x 5 DE + 32 x 5 PSD
   static_assert((SLOTS_ & (SLOTS_ - 1)) == 0, "slot = tile & (kSlots - 1)");
   static_assert((LOAD_ * 4) % 16 == 0 && (LOAD_ / 4) % 2 == 1, "dense rows: LDS.128 conflict-free iff LOAD / 4 is odd");
@@ -57,8 +60,16 @@ struct TmaCfgT {
   static constexpr int smem_bytes(int rows) { return (SLOTS_ * slot_floats(rows) + WARPS_ * kScratchFloats) * 4; }
   static_assert(smem_bytes(kMaxRows) <= 227 * 1024, "shared memory per CTA");
 };
-using TmaCfg500 = TmaCfgT<100, 7, 50, 4, kHannHalfSec, EEGFE_TMA_SLOTS, EEGFE_TMA_WARPS>;
-using TmaCfgWin100 = TmaCfgT<100, 1, 0, 4, kHannHalfSec, EEGFE_TMA_SLOTS, EEGFE_TMA_WARPS>;
+#ifndef EEGFE_TMA_WARPS_NI8
+#define EEGFE_TMA_WARPS_NI8 12
+#endif
+//                               LOAD WIN NWIN HOP NI  HANN          SLOTS            WARPS                MAXROWS
+using TmaCfg500 = TmaCfgT<100, 100, 7, 50, 4, kHannHalfSec, EEGFE_TMA_SLOTS, EEGFE_TMA_WARPS, 64>;
+using TmaCfgWin100 = TmaCfgT<100, 100, 1, 0, 4, kHannHalfSec, EEGFE_TMA_SLOTS, EEGFE_TMA_WARPS, 64>;
+// 200-sample windows: rows of 204 floats (204 / 4 = 51 is odd; the 4 surplus samples are fetched, never read)
+using TmaCfgOneSec = TmaCfgT<204, 200, 2, 200, 8, kHannOneSec, 4, EEGFE_TMA_WARPS_NI8, 62>;
+using TmaCfgTwoSec = TmaCfgT<204, 200, 1, 0, 8, kHannTwoSec, 4, EEGFE_TMA_WARPS_NI8, 62>;
+using TmaCfgWin200 = TmaCfgT<204, 200, 1, 0, 8, kHannOneSec, 4, EEGFE_TMA_WARPS_NI8, 62>;
 
 struct TmaJob {
   CUtensorMap map;          // (time, channel, block) over the recording; box = (kLoad, rows_per_tile, 1)
@@ -72,6 +83,8 @@ struct TmaJob {
   int base, s1, s2;
   unsigned d1, d2;
   int rows_mode;            // 1: tile t is rows [t R, t R + R) of a dense (n_rows, kLoad) array
+  const float* in;          // the recording again, for the windows TMA cannot fetch (8-byte aligned starts)
+  long long block_stride, ch_stride;
 };
 
 __device__ __forceinline__ void tma_load_box(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
@@ -81,6 +94,16 @@ __device__ __forceinline__ void tma_load_box(void* dst_smem, const CUtensorMap* 
           smem_u32(dst_smem)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
+}
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+// this thread's earlier cp.async land -> one arrival on `bar` (.noinc: counted against the barrier's init count)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
+{
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <class TC>
@@ -110,7 +133,8 @@ __global__ void __launch_bounds__(TC::kThreads, 1) de_psd_tma_kernel(const __gri
   float* const out_psd = job.psd + unit_lo * 5;
   const unsigned box_bytes = R * TC::kLoad * 4;
 
-  // one lane: arm the slot's barrier and issue the tensor copy of local tile t
+  // whole warp: arm the slot's barrier (32 arrivals per phase) and fetch local tile t -- one tensor copy when the
+  // window starts on a 16-byte boundary, else 8-byte cp.async (two per row: 32 + 18 lanes x 8 B = 400 B)
   auto load_tile = [&](unsigned t, unsigned generation) {
     const unsigned s = t & (TC::kSlots - 1);
     int x, y, z;
@@ -129,16 +153,36 @@ __global__ void __launch_bounds__(TC::kThreads, 1) de_psd_tma_kernel(const __gri
       y = 0;
       z = static_cast<int>(q);
     }
-    fence_proxy_async_smem();              // generic-proxy reads of the slot happen-before the async-proxy refill
-    mbar_arrive_expect_tx(&full_bar[s], box_bytes);
-    st_release_smem(&armed[s], generation + 1u);
-    tma_load_box(ring + s * slot_floats, &job.map, x, y, z, &full_bar[s]);
+    float* const dst = ring + s * slot_floats;
+    if (lane == 0) st_release_smem(&armed[s], generation + 1u);
+    if ((x & 3) == 0) {
+      if (lane == 0) {
+        fence_proxy_async_smem();            // generic-proxy reads of the slot happen-before the async-proxy refill
+        mbar_arrive_expect_tx(&full_bar[s], box_bytes);
+        tma_load_box(dst, &job.map, x, y, z, &full_bar[s]);
+      } else {
+        mbar_arrive(&full_bar[s]);
+      }
+    } else {
+      if constexpr (TC::kLoad == 100) {
+        const float* src = job.in + static_cast<long long>(z) * job.block_stride + x + 2 * lane;
+        float* d = dst + 2 * lane;
+#pragma unroll 2
+        for (unsigned row = 0; row < R; ++row) {
+          cp_async8(d, src);
+          if (lane < 18) cp_async8(d + 64, src + 64);
+          src += job.ch_stride;
+          d += TC::kLoad;
+        }
+      }
+      cp_async_arrive(&full_bar[s]);
+    }
   };
 
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < TC::kSlots; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 32);
       armed[s] = 0;
       consumed[s] = 0;
     }
@@ -148,7 +192,7 @@ __global__ void __launch_bounds__(TC::kThreads, 1) de_psd_tma_kernel(const __gri
   __syncthreads();
   {
     const unsigned w = threadIdx.x >> 5;
-    if (w < TC::kSlots && w < n_tiles && lane == 0) load_tile(w, 0u);
+    if (w < TC::kSlots && w < n_tiles) load_tile(w, 0u);
   }
 
   for (;;) {
@@ -179,15 +223,18 @@ __global__ void __launch_bounds__(TC::kThreads, 1) de_psd_tma_kernel(const __gri
     // ---- retire: count this warp's lanes into every tile they came from; whoever completes a tile refills its slot ----
     for (unsigned tk = t_first; tk <= t_last; ++tk) {
       const unsigned cnt = __popc(__ballot_sync(0xffffffffu, valid && t == tk));
+      unsigned last = 0;
       if (lane == 0) {
         const unsigned s = tk & (TC::kSlots - 1);
         const unsigned left = n_units - tk * R;
         const unsigned rows_here = left < R ? left : R;
         if (atom_add_acq_rel_smem(&consumed[s], cnt) + cnt == rows_here) {
           consumed[s] = 0;
-          if (tk + TC::kSlots < n_tiles) load_tile(tk + TC::kSlots, tk / TC::kSlots + 1);
+          last = 1;
         }
       }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last && tk + TC::kSlots < n_tiles) load_tile(tk + TC::kSlots, tk / TC::kSlots + 1);
     }
     // ---- results: [lane][band] -> scratch -> consecutive lanes store consecutive floats (one run of 160 per array) ----
     if (valid) {
