@@ -17,6 +17,7 @@
 //                      gather / sliding-window / statistics kernels for the materialising and "next row" entry points
 //
 // C ABI: include/eegfe.h.  Reference semantics: see the citations in that header and in bandpower.cuh.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -32,6 +33,9 @@ namespace eegfe {
 // job description shared by all feature kernels
 // ---------------------------------------------------------------------------------------------------------------
 struct Job {
+  // (time, channel, block) tensor map over the input for the kernels that fetch a tile with ONE TMA tensor copy
+  // (valid iff tiles_per_clip > 0 or rows_tma); first member: the TMA unit wants it 64-byte aligned in param space
+  CUtensorMap map;
   const float* in;
   float* de;
   float* psd;
@@ -44,6 +48,8 @@ struct Job {
   unsigned d1, d2;
   unsigned n_ch;
   long long t_extent;     // valid elements of a channel row (tensor-map bound of the time axis); 0 = unknown
+  unsigned tiles_per_clip;  // > 0: tiles never straddle clips (tile = kRows channels of one clip), fetched as tensor boxes
+  int rows_tma;             // pre-cut windows in a dense / uniformly strided 2-D array: tile = tensor box of kRows rows
   // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = x * scale[ch] + shift[ch]
   float* norm_out;
   const float* norm_scale;
@@ -151,6 +157,18 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// one tiled tensor copy (SASS UTMALDG): box (c0.., c1.., c2) of the tensor map -> dense rows in shared memory.
+// The innermost start c0 must sit on a 16-byte boundary (measured: c0 = 2 floats raises "illegal instruction",
+// tools/microbench/tma_align.cu), which is why the 50-sample hop of the 500 ms windows cannot ride on it.
+__device__ __forceinline__ void tma_load_box(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // row g (32-bit) -> element offset of its first sample, and the index of its first output value
@@ -269,7 +287,6 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
 
 }  // namespace eegfe
 #include "eegfe_stream.cuh"
-#include "eegfe_tma.cuh"
 namespace eegfe {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -291,7 +308,7 @@ namespace eegfe {
 // kSplit == 1: a worker runs both sweeps and the epilogue and stages (de, psd).
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const Job job)
+__global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const __grid_constant__ Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const ring = reinterpret_cast<float*>(smem_raw);
@@ -309,12 +326,22 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
+  // Tiles: kRows consecutive rows -- or, with job.tiles_per_clip (tensor-copy producer), kRows consecutive CHANNELS
+  // of one clip, so that a tile is a rectangle of the (time, channel, block) tensor; a clip's last tile is short.
+  constexpr bool kTensorLoads = (C::kLoad == 200);       // rows that fit one tensor box (inner extent <= 256)
+  const unsigned tpc = kTensorLoads ? job.tiles_per_clip : 0u;
+  const unsigned n_tiles = tpc ? (job.total_rows / job.n_ch) * tpc : (job.total_rows + C::kRows - 1) / C::kRows;
   // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
   const int n_mine = blockIdx.x < n_tiles ? static_cast<int>((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
-  auto tile_row0 = [&](int m) { return (blockIdx.x + static_cast<unsigned>(m) * gridDim.x) * C::kRows; };
+  auto tile_row0 = [&](int m) {
+    const unsigned gt = blockIdx.x + static_cast<unsigned>(m) * gridDim.x;
+    if (tpc == 0) return gt * C::kRows;
+    const unsigned clip = gt / tpc;
+    return clip * job.n_ch + (gt - clip * tpc) * C::kRows;
+  };
   auto tile_nrows = [&](unsigned row0) {
-    const unsigned left = job.total_rows - row0;
+    unsigned left = job.total_rows - row0;
+    if (tpc) left = job.n_ch - row0 % job.n_ch;          // rows to the end of the clip
     return static_cast<int>(left < C::kRows ? left : C::kRows);
   };
 
@@ -344,6 +371,27 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       mbar_wait(&empty_bar[s], ((m / C::kSlots) & 1) ^ 1);
       const unsigned row0 = tile_row0(m);
       const unsigned nrows = tile_nrows(row0);
+      if (kTensorLoads && (tpc != 0 || job.rows_tma)) {
+        // ONE tensor copy per tile: box (kRowStride samples, kRows rows) -> exactly the slot's padded rows.  Rows past
+        // the clip's last channel / the array's last row are out of bounds: zero-filled, never read.
+        if (lane == 0) {
+          int x = 0, y = static_cast<int>(row0), z = 0;
+          if (tpc != 0) {
+            const unsigned u = row0 / job.n_ch;
+            const unsigned q = u / job.d1;
+            const unsigned rem = u - q * job.d1;
+            const unsigned c = rem / job.d2;
+            x = static_cast<int>(job.base) + static_cast<int>(c) * job.s1 + static_cast<int>(rem - c * job.d2) * job.s2;
+            y = static_cast<int>(row0 - u * job.n_ch);
+            z = static_cast<int>(q);
+          }
+          mbar_arrive_expect_tx(&full_bar[s], C::kRows * C::kRowStride * 4);
+          st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
+          tma_load_box(ring + s * C::kSlotFloats, &job.map, x, y, z, &full_bar[s]);
+        }
+        __syncwarp();
+        continue;
+      }
       if (lane == 0) {
         mbar_arrive_expect_tx(&full_bar[s], nrows * C::kRowBytes);
         st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
@@ -690,109 +738,79 @@ static bool legacy_forced()
   return v;
 }
 
-constexpr int kTmaNotApplicable = -1000;     // internal: the caller falls back to the 1-D bulk-copy kernels
-
-// Returns kTmaNotApplicable when this job cannot use the window-box kernel (shape, alignment, driver).
-template <class TC>
-static int launch_tma(const Job& job, cudaStream_t stream)
+#ifndef EEGFE_TMA_L2_PROMOTION
+#define EEGFE_TMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_NONE
+#endif
+// Tensor map for the ring kernel's tensor-copy producer (200-sample rows: 2 s mode, pre-cut 1 s / 2 s windows).
+// Fills job.map and job.tiles_per_clip / job.rows_tma; returns false when the job has to stay on per-row bulk copies
+// (few channels, aliased blocks, no driver support).  L2 promotion NONE: a 2 s row is 800 B out of every 1600 B, and
+// with the 128-byte promotion of the 1-D bulk copies DRAM read 896 B of it (profiles/ncu_traffic.json, round 1).
+template <class C>
+static bool attach_tensor_map(Job& job)
 {
-  if (job.total_rows == 0) return 0;
-  if (legacy_forced() || job.norm_out != nullptr) return kTmaNotApplicable;
+  job.tiles_per_clip = 0;
+  job.rows_tma = 0;
+  if (legacy_forced()) return false;
   const EncodeTiledFn encode = encode_tiled_fn();
-  if (encode == nullptr) return kTmaNotApplicable;
-  const bool rows_mode = (job.n_ch == 1 && job.d1 == 1 && job.ch_stride == 0 && TC::kWindows == 1);
-  TmaJob tj{};
+  if (encode == nullptr) return false;
+  const bool rows_mode = (job.n_ch == 1 && job.d1 == 1 && job.ch_stride == 0);
   cuuint64_t gdim[3], gstride[2];
-  cuuint32_t box[3], estride[3] = {1, 1, 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(C::kRowStride), static_cast<cuuint32_t>(C::kRows), 1}, estride[3] = {1, 1, 1};
+  unsigned tpc = 0;
   if (rows_mode) {
-    if (job.s0 < TC::kWin || job.base != 0) return kTmaNotApplicable;
-    tj.rows_per_tile = TC::kMaxRows;
-    tj.n_units = job.total_rows;
-    tj.n_groups = (job.total_rows + TC::kMaxRows - 1) / TC::kMaxRows;
-    gdim[0] = TC::kWin;                      // samples past the window are out of bounds: zero-filled, never read
+    if (job.s0 < C::kLoad || job.base != 0) return false;
+    gdim[0] = C::kLoad;                      // samples past the window are out of bounds: zero-filled, never read
     gdim[1] = job.total_rows;
     gdim[2] = 1;
     gstride[0] = static_cast<cuuint64_t>(job.s0) * 4;
     gstride[1] = gstride[0] * job.total_rows;
   } else {
-    if (job.n_ch < 16 || job.n_ch > TC::kMaxRows || job.t_extent <= 0 || job.base < 0) return kTmaNotApplicable;
+    if (job.n_ch < 24 || job.t_extent <= 0 || job.base < 0) return false;
     const unsigned n_clips = job.total_rows / job.n_ch;
     const unsigned n_blocks = (n_clips + job.d1 - 1) / job.d1;
-    tj.rows_per_tile = job.n_ch;
-    tj.n_groups = n_clips;
-    tj.n_units = static_cast<unsigned long long>(n_clips) * TC::kWindows * job.n_ch;
+    if (n_blocks > 1 && job.s0 <= 0) return false;          // aliased blocks (stride 0): no tensor view
+    tpc = (job.n_ch + C::kRows - 1) / C::kRows;
     gdim[0] = static_cast<cuuint64_t>(job.t_extent);
     gdim[1] = job.n_ch;
     gdim[2] = n_blocks;
     gstride[0] = static_cast<cuuint64_t>(job.ch_stride) * 4;
-    gstride[1] = (n_blocks > 1 && job.s0 > 0) ? static_cast<cuuint64_t>(job.s0) * 4 : gstride[0] * job.n_ch;
+    gstride[1] = n_blocks > 1 ? static_cast<cuuint64_t>(job.s0) * 4 : gstride[0] * job.n_ch;
   }
-  if (gstride[0] % 16 != 0 || gstride[1] % 16 != 0 || gstride[0] >= (1ull << 40) || gstride[1] >= (1ull << 40) ||
-      gdim[0] > (1ull << 32) || gdim[1] > (1ull << 32) || gdim[2] > (1ull << 32))
-    return kTmaNotApplicable;
-  box[0] = TC::kLoad;
-  box[1] = tj.rows_per_tile;
-  box[2] = 1;
-#ifndef EEGFE_TMA_L2_PROMOTION
-#define EEGFE_TMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-#endif
-  if (encode(&tj.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(job.in), gdim, gstride, box, estride,
+  if (gstride[0] == 0 || gstride[0] % 16 != 0 || gstride[1] % 16 != 0 || gstride[0] >= (1ull << 40) ||
+      gstride[1] >= (1ull << 40) || gdim[0] > (1ull << 32) || gdim[1] > (1ull << 32) || gdim[2] > (1ull << 32))
+    return false;
+  if (encode(&job.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(job.in), gdim, gstride, box, estride,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, EEGFE_TMA_L2_PROMOTION,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return kTmaNotApplicable;
-  tj.de = job.de;
-  tj.psd = job.psd;
-  tj.status = job.status;
-  tj.base = static_cast<int>(job.base);
-  tj.s1 = job.s1;
-  tj.s2 = job.s2;
-  tj.d1 = job.d1;
-  tj.d2 = job.d2;
-  tj.rows_mode = rows_mode ? 1 : 0;
-  tj.in = job.in;
-  tj.block_stride = job.s0;
-  tj.ch_stride = job.ch_stride;
-  const int smem = TC::smem_bytes(static_cast<int>(tj.rows_per_tile));
-  static std::atomic<unsigned long long> configured{0};
-  const int rc = configure_smem(configured, de_psd_tma_kernel<TC>, TC::smem_bytes(TC::kMaxRows));
-  if (rc != 0) return rc;
-  unsigned grid = static_cast<unsigned>(sm_count());
-  if (grid > tj.n_groups) grid = tj.n_groups;
-  de_psd_tma_kernel<TC><<<grid, TC::kThreads, smem, stream>>>(tj);
-  ++g_launches;
-  ++g_tma_launches;
-  return static_cast<int>(cudaGetLastError());
+    return false;
+  job.tiles_per_clip = tpc;
+  job.rows_tma = rows_mode ? 1 : 0;
+  return true;
 }
 
 // One launch over `job.total_rows` rows (< 2^31, output indices < 2^31: guaranteed by run_units()).
 template <class C>
-static int launch(const Job& job, bool aligned16, cudaStream_t stream)
+static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
 {
-  if (job.total_rows == 0) return 0;
-  const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
+  if (job_in.total_rows == 0) return 0;
+  Job job = job_in;
+  job.tiles_per_clip = 0;
+  job.rows_tma = 0;
+  unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (aligned16) {
     if constexpr (C::kLoad == 400 && C::kWindows == 7) {
-      // 500 ms sliding windows: the window-box kernel, else (few / many channels, GLMNet product) the streaming kernel
-      const int rc = launch_tma<TmaCfg500>(job, stream);
-      if (rc != kTmaNotApplicable) return rc;
-      return launch_stream<StreamCfg>(job, stream);
+      return launch_stream<StreamCfg>(job, stream);        // 500 ms sliding windows: the streaming kernel
     } else if constexpr (C::kLoad == 100 && C::kWindows == 1) {
-      // pre-cut 500 ms windows: dense rows
-      const int rc = launch_tma<TmaCfgWin100>(job, stream);
-      if (rc != kTmaNotApplicable) return rc;
-      return launch_stream<StreamCfgWin100>(job, stream);
+      return launch_stream<StreamCfgWin100>(job, stream);  // pre-cut 500 ms windows: the streaming kernel, dense rows
     } else {
       if (job.norm_out != nullptr) return EEGFE_EINVAL;
-#ifndef EEGFE_RING_1S_2S
-      {
-        // 200-sample windows start on 16-byte boundaries: window-box kernel (one TMA tensor copy per tile)
-        int rc = kTmaNotApplicable;
-        if constexpr (C::kWindows == 2) rc = launch_tma<TmaCfgOneSec>(job, stream);
-        else if constexpr (C::kHann == kHannTwoSec) rc = launch_tma<TmaCfgTwoSec>(job, stream);
-        else rc = launch_tma<TmaCfgWin200>(job, stream);
-        if (rc != kTmaNotApplicable) return rc;
+      if constexpr (C::kLoad == 200) {
+        // 200-sample rows at a 204-float pitch are one tensor box per tile
+        if (attach_tensor_map<C>(job)) {
+          ++g_tma_launches;
+          if (job.tiles_per_clip) n_tiles = (job.total_rows / job.n_ch) * job.tiles_per_clip;
+        }
       }
-#endif
       unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
       if (grid > n_tiles) grid = n_tiles;
       static std::atomic<unsigned long long> configured{0};

@@ -192,9 +192,9 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 /* Number of kernels this library has launched since load (gpu_launches accounting in bench.py). */
 int64_t eegfe_launch_count(void);
 
-/* Of those, launches of the window-box kernels (one TMA tensor copy per tile, csrc/eegfe_tma.cuh).  Tests use it to
- * tell that the fast path, not the 1-D bulk-copy fallback, served a call.  Setting EEGFE_LEGACY_KERNELS=1 in the
- * environment before the first call keeps every job on the fallback kernels (A/B measurements). */
+/* Of those, launches whose tiles are fetched by TMA tensor copies (2 s mode, pre-cut 200 / 400-sample windows).  Tests use it to
+ * tell that the tensor-copy producer, not the per-row bulk-copy one, served a call.  Setting EEGFE_LEGACY_KERNELS=1 in the
+ * environment before the first call keeps every job on per-row bulk copies (A/B measurements). */
 int64_t eegfe_tma_launch_count(void);
 
 #ifdef __cplusplus

@@ -302,44 +302,48 @@ def test_streaming_kernel_many_tiles_per_cta():
     assert torch.equal(a[0][3], de_w) and torch.equal(a[1][3], psd_w)
 
 
-def test_window_box_kernel_serves_the_standard_shapes(subject):
-    """The 500 ms jobs of the reference's shapes (16..64 channels, 16-byte aligned rows) run on the window-box kernel
-    (one TMA tensor copy per tile, csrc/eegfe_tma.cuh); other channel counts run on the 1-D bulk-copy kernel.  Both
-    use the same arithmetic core, so they must agree bit for bit, channel for channel."""
+def test_tensor_copy_producer_serves_the_200_sample_rows(subject):
+    """2 s mode and pre-cut 200 / 400-sample windows fetch a tile with ONE TMA tensor copy (clip-aligned tiles,
+    csrc/eegfe_kernels.cu `attach_tensor_map`); jobs with fewer than 24 channels stay on per-row bulk copies.  Same
+    arithmetic either way: bit-identical, channel for channel."""
     raw, _ = subject
     before = _lib.tma_launch_count()
-    de, psd = frontend.de_psd_from_raw(raw[:2], "500ms")
+    de, psd = frontend.de_psd_from_raw(raw[:2], "2s")
     assert _lib.tma_launch_count() == before + 1
-    wide = torch.cat([raw[:2], raw[:2, :10]], dim=1).contiguous()                   # 72 channels -> fallback kernel
+    few = raw[:2, :20].contiguous()                                                  # 20 channels -> bulk-copy producer
     before = _lib.tma_launch_count()
-    de_w, psd_w = frontend.de_psd_from_raw(wide, "500ms")
+    de_f, psd_f = frontend.de_psd_from_raw(few, "2s")
     assert _lib.tma_launch_count() == before
-    assert torch.equal(de_w[..., :62, :], de) and torch.equal(psd_w[..., :62, :], psd)
-    assert torch.equal(de_w[..., 62:, :], de[..., :10, :])
-    # pre-cut windows: dense rows -> window-box kernel, strided rows whose pitch is not a multiple of 16 bytes -> fallback
-    wins = frontend.sliding_windows(frontend.segment_clips(raw[:1])).reshape(-1, 100)
+    assert torch.equal(de_f, de[..., :20, :]) and torch.equal(psd_f, psd[..., :20, :])
+    # pre-cut windows: uniformly strided rows -> tensor boxes; a pitch that is not a multiple of 16 bytes -> fallback
+    clips = frontend.segment_clips(raw[:1])
     before = _lib.tma_launch_count()
-    a = ops.de_psd_windows(wins)
+    a = ops.de_psd_windows(clips.reshape(-1, 400))
     assert _lib.tma_launch_count() == before + 1
-    padded = torch.empty((wins.shape[0], 102), device=DEV)
-    padded[:, :100] = wins
-    b = ops.de_psd_windows(padded[:, :100])
+    assert torch.equal(a[0].reshape(de[0].shape), de[0]) and torch.equal(a[1].reshape(de[0].shape), psd[0])
+    padded = torch.empty((clips.numel() // 400, 402), device=DEV)
+    padded[:, :400] = clips.reshape(-1, 400)
+    b = ops.de_psd_windows(padded[:, :400])
     assert _lib.tma_launch_count() == before + 1
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-    assert torch.equal(a[0].reshape(de[0].shape), de[0])
+    one = ops.de_psd_windows(clips.reshape(-1, 200))                                 # 1 s windows, dense rows
+    de1, psd1 = frontend.de_psd_from_raw(raw[:1], "1s")
+    shape = (1, 40, 5, 62, 2, 5)                                                     # rows run (clip, channel, half)
+    assert torch.equal(one[0].reshape(shape).permute(0, 1, 2, 4, 3, 5), de1)
+    assert torch.equal(one[1].reshape(shape).permute(0, 1, 2, 4, 3, 5), psd1)
 
 
-@pytest.mark.parametrize("n_clips,n_ch", ((1, 16), (147, 20), (149, 33), (300, 48), (1000, 62), (2077, 64), (31, 63)))
-def test_window_box_kernel_ragged(n_clips, n_ch):
-    """Window-box kernel: fewer clips than SMs, clip counts that do not divide by the grid, passes that straddle
-    two or three tiles (n_ch < 32), slot recycling (many tiles per CTA) -- against the float64 closed form."""
+@pytest.mark.parametrize("n_clips,n_ch", ((1, 24), (3, 31), (147, 32), (149, 33), (300, 48), (1000, 62), (700, 64),
+                                          (31, 65), (40, 100)))
+def test_clip_aligned_tiles_ragged(n_clips, n_ch):
+    """2 s ring kernel with tensor boxes: tiles are 32 channels of ONE clip, the last tile of a clip is short (62 = 32
+    + 30, 65 = 32 + 32 + 1); fewer tiles than CTAs, tile counts that do not divide by the grid, slot recycling."""
     rng = np.random.default_rng(77 * n_clips + n_ch)
     clips = (30 * rng.standard_normal((n_clips, n_ch, 400)) + rng.uniform(-50, 50, (n_clips, n_ch, 1))).astype(np.float32)
     before = _lib.tma_launch_count()
-    de, psd = frontend.de_psd_from_clips(torch.from_numpy(clips).to(DEV), "500ms")
+    de, psd = frontend.de_psd_from_clips(torch.from_numpy(clips).to(DEV), "2s")
     assert _lib.tma_launch_count() == before + 1
-    wins = np.stack([clips[..., 50 * w:50 * w + 100] for w in range(7)], axis=1)
-    de_ref, psd_ref = oracle.de_psd_closed_form(wins, 200, 0.5)
+    de_ref, psd_ref = oracle.de_psd_closed_form(clips, 200, 2)
     assert_features_close(de.cpu().numpy(), psd.cpu().numpy(), de_ref, psd_ref)
 
 
