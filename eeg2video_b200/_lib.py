@@ -36,6 +36,7 @@ SIGNATURES = {
                                      ctypes.POINTER(_int)]),
     "eegfe_launch_count": (_i64, []),
     "eegfe_tma_launch_count": (_i64, []),
+    "eegfe_set_tensor_loads": (_int, [_int]),
 }
 
 _lib = None
@@ -82,6 +83,11 @@ def launch_count():
 
 def tma_launch_count():
     return int(load().eegfe_tma_launch_count())
+
+
+def set_tensor_loads(on):
+    """Switch the 200-sample-row kernels to one TMA tensor copy per tile (measurement option); returns the old value."""
+    return bool(load().eegfe_set_tensor_loads(int(bool(on))))
 
 
 def launch_geometry(mode):

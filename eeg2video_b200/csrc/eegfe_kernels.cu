@@ -729,14 +729,14 @@ static EncodeTiledFn encode_tiled_fn()
   return fn;
 }
 
-static bool legacy_forced()
-{
-#ifdef EEGFE_FORCE_LEGACY
-  return true;
+// Tensor-copy producer of the ring kernel: OFF unless switched on (eegfe_set_tensor_loads / -DEEGFE_TENSOR_LOADS=1).
+// Measured on B200 (tools/kbench.py, 24 subjects, 2 s mode): 6.0 G channel-windows/s with one tensor copy per
+// clip-aligned tile against 6.85 G with one bulk copy per row, whatever the L2 promotion -- so it is kept for
+// measurements (DRAM traffic with sector-granular fetches), not as the default.
+#ifndef EEGFE_TENSOR_LOADS
+#define EEGFE_TENSOR_LOADS 0
 #endif
-  static const bool v = [] { const char* e = getenv("EEGFE_LEGACY_KERNELS"); return e != nullptr && e[0] == '1'; }();
-  return v;
-}
+static std::atomic<int> g_tensor_loads{EEGFE_TENSOR_LOADS};
 
 #ifndef EEGFE_TMA_L2_PROMOTION
 #define EEGFE_TMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_NONE
@@ -750,7 +750,7 @@ static bool attach_tensor_map(Job& job)
 {
   job.tiles_per_clip = 0;
   job.rows_tma = 0;
-  if (legacy_forced()) return false;
+  if (g_tensor_loads.load(std::memory_order_relaxed) == 0) return false;
   const EncodeTiledFn encode = encode_tiled_fn();
   if (encode == nullptr) return false;
   const bool rows_mode = (job.n_ch == 1 && job.d1 == 1 && job.ch_stride == 0);
@@ -1220,5 +1220,10 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 int64_t eegfe_launch_count(void) { return g_launches.load(); }
 
 int64_t eegfe_tma_launch_count(void) { return g_tma_launches.load(); }
+
+int eegfe_set_tensor_loads(int on)
+{
+  return g_tensor_loads.exchange(on ? 1 : 0);
+}
 
 }  // extern "C"

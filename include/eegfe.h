@@ -192,9 +192,11 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 /* Number of kernels this library has launched since load (gpu_launches accounting in bench.py). */
 int64_t eegfe_launch_count(void);
 
-/* Of those, launches whose tiles are fetched by TMA tensor copies (2 s mode, pre-cut 200 / 400-sample windows).  Tests use it to
- * tell that the tensor-copy producer, not the per-row bulk-copy one, served a call.  Setting EEGFE_LEGACY_KERNELS=1 in the
- * environment before the first call keeps every job on per-row bulk copies (A/B measurements). */
+/* Tile loader of the 200-sample-row kernels (2 s mode, pre-cut 200 / 400-sample windows).  Default (0): one 1-D TMA
+ * bulk copy per row.  1: clip-aligned tiles fetched by ONE TMA tensor copy each (cp.async.bulk.tensor, tensor map built
+ * per launch, L2 promotion off) -- slower on B200 (6.0 vs 6.85 G channel-windows/s in 2 s mode), kept for traffic
+ * measurements.  Process-wide; returns the previous setting.  eegfe_tma_launch_count(): launches that used it. */
+int eegfe_set_tensor_loads(int on);
 int64_t eegfe_tma_launch_count(void);
 
 #ifdef __cplusplus

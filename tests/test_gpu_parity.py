@@ -302,14 +302,26 @@ def test_streaming_kernel_many_tiles_per_cta():
     assert torch.equal(a[0][3], de_w) and torch.equal(a[1][3], psd_w)
 
 
-def test_tensor_copy_producer_serves_the_200_sample_rows(subject):
-    """2 s mode and pre-cut 200 / 400-sample windows fetch a tile with ONE TMA tensor copy (clip-aligned tiles,
-    csrc/eegfe_kernels.cu `attach_tensor_map`); jobs with fewer than 24 channels stay on per-row bulk copies.  Same
-    arithmetic either way: bit-identical, channel for channel."""
+@pytest.fixture
+def tensor_loads():
+    old = _lib.set_tensor_loads(True)
+    yield
+    _lib.set_tensor_loads(old)
+
+
+def test_tensor_copy_producer_serves_the_200_sample_rows(subject, tensor_loads):
+    """Measurement option eegfe_set_tensor_loads(1): 2 s mode and pre-cut 200 / 400-sample windows fetch a tile with
+    ONE TMA tensor copy (clip-aligned tiles, csrc/eegfe_kernels.cu `attach_tensor_map`); jobs with fewer than 24
+    channels stay on per-row bulk copies.  Same arithmetic either way: bit-identical, channel for channel."""
     raw, _ = subject
+    _lib.set_tensor_loads(False)
     before = _lib.tma_launch_count()
+    de0, psd0 = frontend.de_psd_from_raw(raw[:2], "2s")                              # the default: per-row bulk copies
+    assert _lib.tma_launch_count() == before
+    _lib.set_tensor_loads(True)
     de, psd = frontend.de_psd_from_raw(raw[:2], "2s")
     assert _lib.tma_launch_count() == before + 1
+    assert torch.equal(de, de0) and torch.equal(psd, psd0)
     few = raw[:2, :20].contiguous()                                                  # 20 channels -> bulk-copy producer
     before = _lib.tma_launch_count()
     de_f, psd_f = frontend.de_psd_from_raw(few, "2s")
@@ -335,7 +347,7 @@ def test_tensor_copy_producer_serves_the_200_sample_rows(subject):
 
 @pytest.mark.parametrize("n_clips,n_ch", ((1, 24), (3, 31), (147, 32), (149, 33), (300, 48), (1000, 62), (700, 64),
                                           (31, 65), (40, 100)))
-def test_clip_aligned_tiles_ragged(n_clips, n_ch):
+def test_clip_aligned_tiles_ragged(n_clips, n_ch, tensor_loads):
     """2 s ring kernel with tensor boxes: tiles are 32 channels of ONE clip, the last tile of a clip is short (62 = 32
     + 30, 65 = 32 + 32 + 1); fewer tiles than CTAs, tile counts that do not divide by the grid, slot recycling."""
     rng = np.random.default_rng(77 * n_clips + n_ch)
