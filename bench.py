@@ -69,25 +69,53 @@ def _cpu_init(path):
     _CPU_CLIPS = np.load(path, mmap_mode="r")
 
 
+REF_STAGE = os.path.join(ROOT, "baseline", "_ref")          # unmodified copy of the reference's EEG_preprocessing/*.py,
+                                                              # staged by __graft_entry__.build() (git-ignored)
+
+
+_REF_DE_PSD = None
+
+
+def reference_de_psd():
+    """(DE_PSD callable, kind): the reference's own DE_PSD when its files are staged under baseline/_ref (kind
+    "reference"), else the oracle's loop-for-loop port (kind "port")."""
+    global _REF_DE_PSD
+    if _REF_DE_PSD is None:
+        _REF_DE_PSD = _load_reference_de_psd()
+    return _REF_DE_PSD
+
+
+def _load_reference_de_psd():
+    path = os.path.join(REF_STAGE, "EEG_preprocessing", "DE_PSD.py")
+    if os.path.exists(path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_eeg2video_reference_DE_PSD", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.DE_PSD, "reference"
+    import oracle
+    return oracle.de_psd_loop, "port"
+
+
 def _cpu_work(args):
     """Reference arithmetic for `n` clips starting at `first` (500 ms driver loop, 1per500ms.py:20-27)."""
     first, n, mode = args
     import numpy as np
-    import oracle
+    de_psd, _ = reference_de_psd()
     clips = _CPU_CLIPS
     done = 0
     for i in range(first, first + n):
         clip = np.asarray(clips[i % clips.shape[0]])
         if mode == "500ms":
             for w in range(7):
-                oracle.de_psd_loop(clip[:, 50 * w:50 * w + 100], 200, 0.5)
+                de_psd(clip[:, 50 * w:50 * w + 100], 200, 0.5)
             done += 7 * clip.shape[0]
         elif mode == "1s":
-            oracle.de_psd_loop(clip[:, :200], 200, 1)
-            oracle.de_psd_loop(clip[:, 200:], 200, 1)
+            de_psd(clip[:, :200], 200, 1)
+            de_psd(clip[:, 200:], 200, 1)
             done += 2 * clip.shape[0]
         else:
-            oracle.de_psd_loop(clip, 200, 2)
+            de_psd(clip, 200, 2)
             done += clip.shape[0]
     return done
 
@@ -101,6 +129,9 @@ class CpuArm:
         from eeg2video_b200 import synth
         import oracle
         self.mode = mode
+        self.kind = reference_de_psd()[1]
+        self.what = ("the reference's own EEG_preprocessing/DE_PSD.py (unmodified copy under baseline/_ref)"
+                     if self.kind == "reference" else "oracle.de_psd_loop (loop-for-loop port of DE_PSD.py:8-71)")
         try:
             self.cores = len(os.sched_getaffinity(0))
         except AttributeError:
@@ -146,13 +177,13 @@ def run_reference_arm(args):
     arm.close()
     value = total_cw / total_s
     sample = (f"{args.steps} steps x {arm.cores} workers x {per_step} synthetic 2 s clips (62 ch) each, "
-              f"mode {args.mode}, oracle.de_psd_loop (loop-for-loop port of DE_PSD.py:8-71)")
+              f"mode {args.mode}, {arm.what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, None),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,7 +211,7 @@ def workload_config(args, geometry):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md clocks line)."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -198,9 +229,20 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, windows=None):
+        """Summary over all samples; `windows` = {name: (t0, t1)} (time.time() bounds) adds one summary per window,
+        from the samples whose own timestamp falls inside it."""
+        empty = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return (empty, {k: dict(empty) for k in windows}) if windows else empty
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -208,26 +250,31 @@ class ClockSampler:
             self.proc.kill()
         self.out.flush()
         self.out.seek(0)
-        sm, smax, power, reasons = [], [], [], set()
+        rows = []
         for row in self.out.read().strip().splitlines():
             cells = [c.strip() for c in row.split(",")]
             if len(cells) < 9:
                 continue
             try:
-                sm.append(float(cells[1]))
-                smax.append(float(cells[2]))
-                power.append(float(cells[3]))
+                rec = (self._epoch(cells[0]), float(cells[1]), float(cells[2]), float(cells[3]))
             except ValueError:
                 continue
-            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                  cells[5:9]):
-                if cell.lower().startswith("active"):
-                    reasons.add(name)
+            flags = [name for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                 "sw_power_cap"), cells[5:9]) if cell.lower().startswith("active")]
+            rows.append(rec + (flags,))
         self.out.close()
         os.unlink(self.out.name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+        def summary(sel):
+            sm = sorted(r[1] for r in sel)
+            reasons = sorted({f for r in sel for f in r[4]})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in sel), default=None),
+                    "power_w_max": max((r[3] for r in sel), default=None), "reasons": reasons, "samples": len(sm)}
+        total = summary(rows)
+        if not windows:
+            return total
+        return total, {k: summary([r for r in rows if r[0] is not None and t0 <= r[0] <= t1])
+                       for k, (t0, t1) in windows.items()}
 
 
 def measured_peaks():
@@ -281,9 +328,9 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- parity gate on this rank's first subject (oracle = checker only) ----
+    # ---- parity gate on EVERY rank's first subject (oracle = checker only); the line reports the worst rank ----
     parity = None
-    if rank == 0 and not args.skip_parity:
+    if not args.skip_parity:
         import numpy as np
         import oracle
         blocks = raw[:1]
@@ -296,11 +343,15 @@ def run_gpu_arm(args):
         de_ref, psd_ref = oracle.de_psd_closed_form(wins, 200, tw)
         got_de = de.cpu().numpy().reshape(de_ref.shape)
         got_psd = psd.cpu().numpy().reshape(psd_ref.shape)
-        parity = {"segmentation_bit_exact": seg_ok,
-                  "psd_max_rel": float(np.max(np.abs(got_psd - psd_ref) / psd_ref)),
-                  "de_max_abs": float(np.max(np.abs(got_de - de_ref))),
-                  "checked_channel_windows": int(de_ref.size // 5)}
-        if not (seg_ok and parity["psd_max_rel"] <= 1e-4 and parity["de_max_abs"] <= 1e-4):
+        mine = [0.0 if seg_ok else 1.0, float(np.max(np.abs(got_psd - psd_ref) / psd_ref)),
+                float(np.max(np.abs(got_de - de_ref)))]
+        if world > 1:
+            t = torch.tensor(mine, dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mine = [float(v) for v in t.tolist()]
+        parity = {"segmentation_bit_exact": mine[0] == 0.0, "psd_max_rel": mine[1], "de_max_abs": mine[2],
+                  "checked_channel_windows": int(de_ref.size // 5) * world, "ranks_checked": world}
+        if not (parity["segmentation_bit_exact"] and parity["psd_max_rel"] <= 1e-4 and parity["de_max_abs"] <= 1e-4):
             raise SystemExit(f"parity gate failed: {parity}")
 
     # ---- device-resident throughput: K launches of the fused kernel, CUDA events on the launch stream ----
@@ -316,6 +367,13 @@ def run_gpu_arm(args):
                                              mode_id, de_buf.data_ptr(), psd_buf.data_ptr(), status.data_ptr(),
                                              stream.cuda_stream))
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -327,28 +385,46 @@ def run_gpu_arm(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.nvtx.range_push("eegfe_timed")        # ncu --nvtx --nvtx-include "eegfe_timed/" lists exactly this region
+    t_burst0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
     torch.cuda.nvtx.range_pop()
     barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    t_burst1 = time.time()
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
     gpu_launches = _lib.launch_count() - launches_before
-    # keep the same launches running (untimed) long enough for nvidia-smi to see the clocks under this load
-    if rank == 0:
-        t_end = time.perf_counter() + args.clock_probe_s
-        while time.perf_counter() < t_end:
-            for _ in range(10):
-                step()
-            torch.cuda.synchronize()
-        clocks = sampler.stop()
-        clocks["sampled_over"] = f"timed region + {args.clock_probe_s:.1f} s continuation of the same launches"
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     value = world * cw_step_gpu * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- the same launches back to back for >= args.sustain_s seconds, on every rank: the throughput the 1 kW power
+    #      cap allows (`value` above is a ~25 ms burst entered from idle), timed with CUDA events like `value`, with
+    #      the SM clock sampled over exactly this window ----
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s / (elapsed_ms * 1e-3 / args.steps)) + 1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_sus0 = time.time()
+        e0.record(stream)
+        for _ in range(n_sus):
+            step()
+        e1.record(stream)
+        barrier()
+        t_sus1 = time.time()
+        sus_ms = max_over_ranks(e0.elapsed_time(e1))
+        sustained = {"value": world * cw_step_gpu * n_sus / (sus_ms * 1e-3), "unit": UNIT, "steps": n_sus,
+                     "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus}
+    if rank == 0:
+        windows = {"burst": (t_burst0, t_burst1)}
+        if sustained is not None:
+            # skip the first 0.3 s: the clock is still settling from the burst level
+            windows["sustained"] = (t_sus0 + min(0.3, 0.25 * (t_sus1 - t_sus0)), t_sus1)
+        clocks, per_window = sampler.stop(windows)
+        clocks["sampled_over"] = "timed region + the sustained continuation of the same launches (nvidia-smi, 50 ms period)"
+        clocks["timed_region_only"] = per_window["burst"]
+        if sustained is not None:
+            sustained["clocks"] = per_window["sustained"]
 
     # ---- BASELINE configs[1] as written: ONE subject, one launch (latency-bound; SURVEY.md 8d asks for us per call) ----
     single = None
@@ -521,13 +597,28 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * cw_step_gpu * e2e_steps / e2e_s
-    e2e_ok = bool(torch.equal(de_host, de_buf.cpu())) if rank == 0 else True
+    e2e_ok_local = bool(torch.equal(de_host, de_buf.cpu()) and torch.equal(psd_host, psd_buf.cpu()))
+    e2e_ok = max_over_ranks(0.0 if e2e_ok_local else 1.0) == 0.0           # every rank's host result == its device result
     e2e_launches = _lib.launch_count() - launches_e2e0
 
-    # ---- final gather of the feature tensors to rank 0 (the only collective; reported, not in `value`) ----
+    # ---- final gather of the feature tensors to rank 0 (the only exchange; reported, not in `value`) ----
+    def check_every_rank(full_de, full_psd, per_rank, pick):
+        """rank 0: recompute one subject of EVERY rank's shard locally (subjects are seeded by global id) and compare
+        it with what arrived over NVLink.  Returns (all ranks match, ranks checked)."""
+        ok = True
+        for r in range(world):
+            sid = r * per_rank + pick(r)
+            blocks = synth.synth_subject(sid, device=dev)
+            w_de, w_psd, _ = ops.de_psd_from_raw(blocks, mode_id)
+            ok = ok and bool(torch.equal(full_de[sid].reshape(w_de.shape), w_de) and
+                             torch.equal(full_psd[sid].reshape(w_psd.shape), w_psd))
+        return ok, world
+
     gather = None
     if world > 1:
-        reps = 3
+        raw5 = raw.reshape(S, 7, 62, 104000)
+        # (a) baseline: the plain collective -- NCCL gather of DE and of PSD after the kernels
+        reps = 2
         for i in range(1 + reps):                 # first pass warms up the NCCL channels, untimed
             if i == 1:
                 barrier()
@@ -537,17 +628,104 @@ def run_gpu_arm(args):
             full_psd = cohort.gather_to_rank0(psd_buf.reshape((S, -1)), S * world)
         g1.record()
         barrier()
-        gather_ok = True
-        if rank == 0:
-            gather_ok = bool(torch.equal(full_de[:S].reshape(de_buf.shape), de_buf))
-        gms = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        nbytes = 2 * de_buf.numel() * 4 * (world - 1)
-        gather = {"ms": float(gms.item()), "bytes_into_rank0": nbytes,
-                  "gbs_into_rank0": nbytes / (float(gms.item()) * 1e-3) / 1e9,
-                  "value_with_gather": world * cw_step_gpu / ((elapsed_ms / args.steps + float(gms.item())) * 1e-3),
-                  "rank0_slice_matches": gather_ok}
+        both_ok = check_every_rank(full_de, full_psd, S, lambda r: (3 * r + 1) % S)[0] if rank == 0 else True
+        both_ms = max_over_ranks(g0.elapsed_time(g1) / reps)
         del full_de, full_psd
+        # (b) the product path, compute INCLUDED: cohort.process_cohort -- chunked kernels, PSD only over point-to-point
+        #     NCCL as each chunk finishes, DE rebuilt on rank 0 (eegfe_de_from_psd)
+        chunk = max(1, S // args.gather_chunks)
+        for i in range(1 + reps):
+            if i == 1:
+                barrier()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+            full_de, full_psd = cohort.process_cohort(raw5, S * world, mode=mode, chunk_subjects=chunk)
+        p1.record()
+        barrier()
+        psd_ms = max_over_ranks(p0.elapsed_time(p1) / reps)
+        all_ok, n_checked = (True, world)
+        if rank == 0:
+            all_ok, n_checked = check_every_rank(full_de, full_psd, S, lambda r: (5 * r + 2) % S)
+            all_ok = all_ok and bool(torch.equal(full_de[:S].reshape(de_buf.shape), de_buf))
+        del full_de, full_psd
+        psd_bytes = psd_buf.numel() * 4 * (world - 1)
+        kernel_ms_step = elapsed_ms / args.steps
+        gather = {
+            "path": f"cohort.process_cohort: kernels in {args.gather_chunks} chunks per rank, PSD only over point-to-point "
+                    "NCCL as each chunk finishes, DE rebuilt on rank 0 with the kernels' own log2 expression",
+            "ms_compute_and_gather": psd_ms, "bytes_into_rank0": psd_bytes,
+            "value_with_gather": world * cw_step_gpu / (psd_ms * 1e-3),
+            "gbs_into_rank0": psd_bytes / (max(psd_ms - kernel_ms_step / args.gather_chunks, 1e-3) * 1e-3) / 1e9,
+            "gbs_note": "bytes into rank 0 / (time - first chunk's kernel); NVLink 5 ingest: 900 GB/s nominal, ~770 GB/s "
+                        "measured peer copy (B200_PROFILING.md)",
+            "all_ranks_match": bool(all_ok), "ranks_checked": n_checked,
+            "check": "rank 0 recomputed one subject of every rank's shard from its seed and torch.equal'ed DE and PSD "
+                     "with the gathered slices",
+            "collective_de_and_psd": {
+                "ms": both_ms, "bytes_into_rank0": 2 * psd_bytes, "gbs_into_rank0": 2 * psd_bytes / (both_ms * 1e-3) / 1e9,
+                "value_with_gather": world * cw_step_gpu / ((kernel_ms_step + both_ms) * 1e-3),
+                "all_ranks_match": bool(both_ok),
+                "note": "round-1 path (NCCL gather of both tensors after the kernels), kept as the comparison"}}
+
+    # ---- BASELINE configs[3] as written: the 1000-subject cohort, 500 ms sliding windows, sharded by subject ----
+    cohort_big = None
+    if args.cohort_subjects > 0:
+        total = args.cohort_subjects
+        lo_g, hi_g = cohort.shard_bounds(total, rank, world)
+        n_local = hi_g - lo_g
+        free_b = torch.cuda.mem_get_info(dev)[0]
+        resident = n_local * synth.BYTES_PER_SUBJECT + (n_local + (total if rank == 0 else 0)) * 24.304e6 < 0.8 * free_b
+        k_events = []
+
+        def timed_compute(x):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            out = frontend.de_psd_from_raw(x, mode, check=False)
+            b_.record()
+            k_events.append((a_, b_))
+            return out
+        chunk_c = args.cohort_chunk
+        if resident:
+            del de_buf, psd_buf
+            big = synth.synth_cohort(range(lo_g, hi_g), dev)
+            loader = lambda lo, hi: big[lo:hi]                               # noqa: E731
+        else:
+            stage = torch.empty((chunk_c,) + tuple(raw.reshape(S, 7, 62, 104000).shape[1:]), dtype=torch.float32, device=dev)
+
+            def loader(lo, hi):
+                return synth.synth_cohort(range(lo_g + lo, lo_g + hi), dev, out=stage[:hi - lo])
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        c0.record()
+        big_de, big_psd = cohort.run_cohort(n_local, loader, total, mode=mode, chunk_subjects=chunk_c,
+                                            compute=timed_compute)
+        c1.record()
+        barrier()
+        wall_s = time.perf_counter() - t_wall
+        kernel_s = max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in k_events) * 1e-3)
+        total_s = max_over_ranks(c0.elapsed_time(c1) * 1e-3)
+        big_ok = True
+        if rank == 0:
+            rng_pick = [(7 * r + 3) % max(1, total // world) for r in range(world)]
+            for r in range(world):
+                sid = cohort.shard_bounds(total, r, world)[0] + rng_pick[r]
+                w_de, w_psd = frontend.de_psd_from_raw(synth.synth_subject(sid, device=dev), mode, check=False)
+                big_ok = big_ok and bool(torch.equal(big_de[sid], w_de) and torch.equal(big_psd[sid], w_psd))
+        cw_total = total * CW_PER_SUBJECT[mode]
+        cohort_big = {
+            "subjects": total, "subjects_per_gpu": n_local, "chunk_subjects": chunk_c, "channel_windows": cw_total,
+            "raw_resident": bool(resident),
+            "kernel_seconds": kernel_s, "value_kernels_only": cw_total / kernel_s,
+            "seconds_compute_and_gather": total_s if resident else None,
+            "value_with_gather": cw_total / total_s if resident else None,
+            "wall_seconds_including_synthesis": wall_s,
+            "features_on_rank0_gb": total * 24.304e6 / 1e9,
+            "all_ranks_match": bool(big_ok),
+            "note": ("recordings resident in HBM before the timed region" if resident else
+                     "180 GB of recordings do not fit one GPU: synthesised chunk by chunk inside the loop, so only the "
+                     "kernels are timed (CUDA events per chunk); there is no gather at 1 GPU")}
+        del big_de, big_psd
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -561,20 +739,29 @@ def run_gpu_arm(args):
                     "note": "500 ms mode is bounded by the FP32 pipe, not HBM (DESIGN.md 'Rooflines'); see 'fp32_pipe'"
                     if mode == "500ms" else ""}
         # the CUDA-core FP32 pipe is what actually bounds the 500 ms kernel: 128 lanes/clk/SM at the clock seen under load
-        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        # numerator and denominator from the SAME window: the sustained run and the SM clock sampled during it
+        if sustained is not None and sustained["clocks"].get("sm_mhz"):
+            sm_mhz, fp_ms, fp_window = sustained["clocks"]["sm_mhz"], sustained["ms_per_step"], "sustained run"
+        else:
+            sm_mhz, fp_ms, fp_window = 1965.0, kernel_ms, "timed region at the maximum SM clock (no clock samples)"
         fp_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
-        fp_ach = cw_step_gpu * FP32_LANE_OPS_PER_CW[mode] / (kernel_ms * 1e-3) / 1e12
+        fp_ach = cw_step_gpu * FP32_LANE_OPS_PER_CW[mode] / (fp_ms * 1e-3) / 1e12
         fp32_pipe = {"achieved": fp_ach, "peak": fp_peak, "unit": "T fp32 lane-op/s (an FMA counts once)",
                      "frac": fp_ach / fp_peak, "lane_ops_per_channel_window": FP32_LANE_OPS_PER_CW[mode],
-                     "peak_source": f"148 SMs x 128 lanes x {sm_mhz:.0f} MHz (median SM clock sampled during the run)"}
+                     "window": fp_window,
+                     "peak_source": f"148 SMs x 128 lanes x {sm_mhz:.0f} MHz (median SM clock sampled over the same window)"}
+        if sustained is not None:
+            sus_gbs = sustained["value"] / world * BYTES_PER_CW[mode] / 1e9
+            sustained["hbm_gbs_per_gpu"] = sus_gbs
+            sustained["hbm_frac"] = sus_gbs / peak
         cpu = None
         if not args.skip_cpu_baseline and world == 1:
             arm = CpuArm(mode)
             cw, s = arm.run(args.cpu_clips_per_step * 24)
             arm.close()
-            cpu = {"value": cw / s, "unit": UNIT, "cores": arm.cores, "kind": "port",
+            cpu = {"value": cw / s, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                    "sample": f"{arm.cores} workers x {args.cpu_clips_per_step * 24} synthetic 2 s clips (62 ch) each, "
-                             f"mode {mode}, oracle.de_psd_loop (loop-for-loop port of DE_PSD.py:8-71), {s:.1f} s"}
+                             f"mode {mode}, {arm.what}, {s:.1f} s"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -594,8 +781,12 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu,
             "parity": parity,
         }
+        line["value_sustained"] = None if sustained is None else sustained["value"]
+        line["sustained"] = sustained
         if gather:
             line["gather"] = gather
+        if cohort_big:
+            line["cohort_1000" if args.cohort_subjects == 1000 else f"cohort_{args.cohort_subjects}"] = cohort_big
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -613,7 +804,11 @@ def main():
     ap.add_argument("--chunk-blocks", type=int, default=28, help="blocks per in-flight chunk of the e2e pipeline")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-clips-per-step", type=int, default=40, help="clips per worker per CPU step")
-    ap.add_argument("--clock-probe-s", type=float, default=1.5)
+    ap.add_argument("--sustain-s", "--clock-probe-s", dest="sustain_s", type=float, default=2.0,
+                    help="seconds of back-to-back launches after the timed steps (sustained throughput + clocks); 0 = off")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="kernel chunks per rank in the gather measurement")
+    ap.add_argument("--cohort-subjects", type=int, default=1000, help="BASELINE configs[3] cohort size; 0 = skip")
+    ap.add_argument("--cohort-chunk", type=int, default=25, help="subjects per kernel launch in the cohort run")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--skip-other-modes", action="store_true")

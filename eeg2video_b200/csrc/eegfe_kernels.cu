@@ -644,6 +644,41 @@ __global__ void channel_stats_finish_kernel(const double* __restrict__ partial, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// de = log2(100 psd), elementwise: the SAME device expression the feature kernels use (band_features / store_tile),
+// so a rank that received only PSD over NVLink rebuilds DE bit for bit (cohort gather moves half the bytes).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) de_from_psd_kernel(const float* __restrict__ psd, float* __restrict__ de,
+                                                           long long n, int* status)
+{
+  const long long n4 = n >> 2;
+  bool zero = false;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(psd) | reinterpret_cast<uintptr_t>(de)) % 16 == 0) {
+    for (long long i = t0; i < n4; i += stride) {
+      const float4 p = reinterpret_cast<const float4*>(psd)[i];
+      float4 d;
+      d.x = __log2f(100.0f * p.x);
+      d.y = __log2f(100.0f * p.y);
+      d.z = __log2f(100.0f * p.z);
+      d.w = __log2f(100.0f * p.w);
+      zero |= (p.x == 0.0f) | (p.y == 0.0f) | (p.z == 0.0f) | (p.w == 0.0f);
+      reinterpret_cast<float4*>(de)[i] = d;
+    }
+    for (long long i = 4 * n4 + t0; i < n; i += stride) {
+      zero |= (psd[i] == 0.0f);
+      de[i] = __log2f(100.0f * psd[i]);
+    }
+  } else {
+    for (long long i = t0; i < n; i += stride) {
+      zero |= (psd[i] == 0.0f);
+      de[i] = __log2f(100.0f * psd[i]);
+    }
+  }
+  if (zero && status != nullptr) atomicOr(status, EEGFE_STATUS_ZERO_POWER);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static std::atomic<long long> g_launches{0};
@@ -1014,6 +1049,20 @@ int eegfe_channel_stats(const float* raw, int64_t n_blocks, int n_ch, int64_t bl
     ++g_launches;
   }
   channel_stats_finish_kernel<<<(n_ch + 63) / 64, 64, 0, s>>>(workspace, block_mask, n_blocks, n_ch, mean, std);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+int eegfe_de_from_psd(const float* psd, int64_t n, float* de, int* status, void* stream)
+{
+  if (n < 0) return EEGFE_EINVAL;
+  if (n == 0) return 0;
+  if (psd == nullptr || de == nullptr) return EEGFE_EINVAL;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  de_from_psd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(psd, de, n, status);
   ++g_launches;
   return static_cast<int>(cudaGetLastError());
 }

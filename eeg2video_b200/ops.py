@@ -338,3 +338,16 @@ def standardize(x: torch.Tensor, mean: torch.Tensor, scale: torch.Tensor) -> tor
 @standardize.register_fake
 def _(x, mean, scale):
     return x.new_empty(x.shape)
+
+
+@torch.library.custom_op("eeg2video::de_from_psd", mutates_args=("de",), device_types="cuda")
+def de_from_psd_(psd: torch.Tensor, de: torch.Tensor, status: torch.Tensor) -> None:
+    """de[...] = log2(100 psd) in place of `de` (same shape, float32, contiguous): bit-identical to the DE the feature
+    kernels write next to `psd` (DE_PSD.py:68).  `status` (int32[1]) collects EEGFE_STATUS_ZERO_POWER."""
+    _require_cuda(psd, "psd")
+    if psd.dtype != torch.float32 or de.dtype != torch.float32 or psd.shape != de.shape or \
+            not psd.is_contiguous() or not de.is_contiguous() or de.device != psd.device:
+        raise ValueError("psd and de must be contiguous float32 tensors of one shape on one device")
+    with torch.cuda.device(psd.device):
+        _lib.check(_lib.load().eegfe_de_from_psd(psd.data_ptr(), psd.numel(), de.data_ptr(), status.data_ptr(),
+                                                 _stream(psd)))

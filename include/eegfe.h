@@ -186,6 +186,13 @@ int eegfe_column_stats(const float* x, int64_t n_groups, int64_t n_rows, int n_c
 int eegfe_standardize(const float* x, int64_t n_groups, int64_t n_rows, int n_cols, int64_t row_stride,
                       int64_t group_stride, const double* mean, const double* scale, float* out, void* stream);
 
+/*
+ * DE from PSD, elementwise: de[i] = log2(100 psd[i]) (DE_PSD.py:68) with the device expression of the feature kernels,
+ * so the result is bit-identical to the DE those kernels wrote next to this PSD.  Used by the cohort gather: ranks send
+ * PSD only and rank 0 rebuilds DE (half the NVLink bytes).  Zero power sets EEGFE_STATUS_ZERO_POWER.
+ */
+int eegfe_de_from_psd(const float* psd, int64_t n, float* de, int* status, void* stream);
+
 /* Introspection used by bench.py / tests: kernel launch geometry chosen for `mode` on the current device. */
 int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int* rows_per_tile);
 
