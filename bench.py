@@ -614,45 +614,88 @@ def run_gpu_arm(args):
                              torch.equal(full_psd[sid].reshape(w_psd.shape), w_psd))
         return ok, world
 
+    class ShardKernels:
+        """compute hook for cohort.run_cohort: the fused kernel through the C ABI into PREALLOCATED per-rank feature
+        buffers (chunk after chunk, in call order), one CUDA event pair around each launch -- so that what the events
+        measure is kernels, not the caching allocator."""
+
+        def __init__(self, n_local):
+            shape = (n_local, 7 * 200, ops.WINDOWS_PER_CLIP[mode_id], 62, 5)
+            self.de = torch.empty(shape, dtype=torch.float32, device=dev)
+            self.psd = torch.empty_like(self.de)
+            self.events, self.at = [], 0
+
+        def reset(self):
+            self.events, self.at = [], 0
+
+        def __call__(self, x):
+            n = x.shape[0]
+            flat = x.reshape(n * 7, 62, x.shape[-1])
+            de, psd = self.de[self.at:self.at + n], self.psd[self.at:self.at + n]
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            _lib.check(lib.eegfe_de_psd_from_raw(flat.data_ptr(), flat.shape[0], 62, flat.shape[2], flat.stride(0),
+                                                 flat.stride(1), mode_id, de.data_ptr(), psd.data_ptr(),
+                                                 status.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+            b_.record()
+            self.events.append((a_, b_))
+            self.at += n
+            lead = (n, 7, 40, 5) + ((de.shape[2],) if de.shape[2] > 1 else ()) + (62, 5)
+            return de.reshape(lead), psd.reshape(lead)
+
+        def kernel_seconds(self):
+            return sum(a_.elapsed_time(b_) for a_, b_ in self.events) * 1e-3
+
     gather = None
     if world > 1:
         raw5 = raw.reshape(S, 7, 62, 104000)
+        feat_shape = (S * world, 7, 40, 5) + ((ops.WINDOWS_PER_CLIP[mode_id],) if ops.WINDOWS_PER_CLIP[mode_id] > 1 else ()) + (62, 5)
+        out_full = None
+        if rank == 0:
+            out_full = (torch.empty(feat_shape, dtype=torch.float32, device=dev),
+                        torch.empty(feat_shape, dtype=torch.float32, device=dev))
         # (a) baseline: the plain collective -- NCCL gather of DE and of PSD after the kernels
-        reps = 2
+        reps = 3
+        flat_out = None if out_full is None else (out_full[0].reshape(S * world, -1), out_full[1].reshape(S * world, -1))
         for i in range(1 + reps):                 # first pass warms up the NCCL channels, untimed
             if i == 1:
                 barrier()
                 g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 g0.record()
-            full_de = cohort.gather_to_rank0(de_buf.reshape((S, -1)), S * world)
-            full_psd = cohort.gather_to_rank0(psd_buf.reshape((S, -1)), S * world)
+            cohort.gather_to_rank0(de_buf.reshape((S, -1)), S * world, out=None if flat_out is None else flat_out[0])
+            cohort.gather_to_rank0(psd_buf.reshape((S, -1)), S * world, out=None if flat_out is None else flat_out[1])
         g1.record()
         barrier()
-        both_ok = check_every_rank(full_de, full_psd, S, lambda r: (3 * r + 1) % S)[0] if rank == 0 else True
+        both_ok = check_every_rank(out_full[0], out_full[1], S, lambda r: (3 * r + 1) % S)[0] if rank == 0 else True
         both_ms = max_over_ranks(g0.elapsed_time(g1) / reps)
-        del full_de, full_psd
+        if rank == 0:
+            out_full[0].zero_()
+            out_full[1].zero_()
         # (b) the product path, compute INCLUDED: cohort.process_cohort -- chunked kernels, PSD only over point-to-point
         #     NCCL as each chunk finishes, DE rebuilt on rank 0 (eegfe_de_from_psd)
         chunk = max(1, S // args.gather_chunks)
+        kern = ShardKernels(S)
         for i in range(1 + reps):
             if i == 1:
                 barrier()
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record()
-            full_de, full_psd = cohort.process_cohort(raw5, S * world, mode=mode, chunk_subjects=chunk)
+            kern.reset()
+            cohort.process_cohort(raw5, S * world, mode=mode, chunk_subjects=chunk, compute=kern, out=out_full)
         p1.record()
         barrier()
         psd_ms = max_over_ranks(p0.elapsed_time(p1) / reps)
         all_ok, n_checked = (True, world)
         if rank == 0:
-            all_ok, n_checked = check_every_rank(full_de, full_psd, S, lambda r: (5 * r + 2) % S)
-            all_ok = all_ok and bool(torch.equal(full_de[:S].reshape(de_buf.shape), de_buf))
-        del full_de, full_psd
+            all_ok, n_checked = check_every_rank(out_full[0], out_full[1], S, lambda r: (5 * r + 2) % S)
+            all_ok = all_ok and bool(torch.equal(out_full[0][:S].reshape(de_buf.shape), de_buf))
+        del out_full, flat_out, kern
         psd_bytes = psd_buf.numel() * 4 * (world - 1)
         kernel_ms_step = elapsed_ms / args.steps
         gather = {
             "path": f"cohort.process_cohort: kernels in {args.gather_chunks} chunks per rank, PSD only over point-to-point "
-                    "NCCL as each chunk finishes, DE rebuilt on rank 0 with the kernels' own log2 expression",
+                    "NCCL as each chunk finishes, DE rebuilt on rank 0 with the kernels' own log2 expression; "
+                    "destination tensors preallocated",
             "ms_compute_and_gather": psd_ms, "bytes_into_rank0": psd_bytes,
             "value_with_gather": world * cw_step_gpu / (psd_ms * 1e-3),
             "gbs_into_rank0": psd_bytes / (max(psd_ms - kernel_ms_step / args.gather_chunks, 1e-3) * 1e-3) / 1e9,
@@ -673,24 +716,21 @@ def run_gpu_arm(args):
         total = args.cohort_subjects
         lo_g, hi_g = cohort.shard_bounds(total, rank, world)
         n_local = hi_g - lo_g
+        del de_buf, psd_buf
         free_b = torch.cuda.mem_get_info(dev)[0]
         resident = n_local * synth.BYTES_PER_SUBJECT + (n_local + (total if rank == 0 else 0)) * 24.304e6 < 0.8 * free_b
-        k_events = []
-
-        def timed_compute(x):
-            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a_.record()
-            out = frontend.de_psd_from_raw(x, mode, check=False)
-            b_.record()
-            k_events.append((a_, b_))
-            return out
         chunk_c = args.cohort_chunk
+        kern = ShardKernels(n_local)
+        big_shape = (total, 7, 40, 5) + ((ops.WINDOWS_PER_CLIP[mode_id],) if ops.WINDOWS_PER_CLIP[mode_id] > 1 else ()) + (62, 5)
+        out_big = None
+        if rank == 0:
+            out_big = (torch.empty(big_shape, dtype=torch.float32, device=dev),
+                       torch.empty(big_shape, dtype=torch.float32, device=dev))
         if resident:
-            del de_buf, psd_buf
             big = synth.synth_cohort(range(lo_g, hi_g), dev)
             loader = lambda lo, hi: big[lo:hi]                               # noqa: E731
         else:
-            stage = torch.empty((chunk_c,) + tuple(raw.reshape(S, 7, 62, 104000).shape[1:]), dtype=torch.float32, device=dev)
+            stage = torch.empty((chunk_c, 7, 62, 104000), dtype=torch.float32, device=dev)
 
             def loader(lo, hi):
                 return synth.synth_cohort(range(lo_g + lo, lo_g + hi), dev, out=stage[:hi - lo])
@@ -698,18 +738,18 @@ def run_gpu_arm(args):
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall = time.perf_counter()
         c0.record()
-        big_de, big_psd = cohort.run_cohort(n_local, loader, total, mode=mode, chunk_subjects=chunk_c,
-                                            compute=timed_compute)
+        big_de, big_psd = cohort.run_cohort(n_local, loader, total, mode=mode, chunk_subjects=chunk_c, compute=kern,
+                                            out=out_big)
         c1.record()
         barrier()
         wall_s = time.perf_counter() - t_wall
-        kernel_s = max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in k_events) * 1e-3)
+        kernel_s = max_over_ranks(kern.kernel_seconds())
         total_s = max_over_ranks(c0.elapsed_time(c1) * 1e-3)
         big_ok = True
         if rank == 0:
-            rng_pick = [(7 * r + 3) % max(1, total // world) for r in range(world)]
             for r in range(world):
-                sid = cohort.shard_bounds(total, r, world)[0] + rng_pick[r]
+                r_lo, r_hi = cohort.shard_bounds(total, r, world)
+                sid = r_lo + (7 * r + 3) % max(1, r_hi - r_lo)
                 w_de, w_psd = frontend.de_psd_from_raw(synth.synth_subject(sid, device=dev), mode, check=False)
                 big_ok = big_ok and bool(torch.equal(big_de[sid], w_de) and torch.equal(big_psd[sid], w_psd))
         cw_total = total * CW_PER_SUBJECT[mode]
@@ -721,11 +761,12 @@ def run_gpu_arm(args):
             "value_with_gather": cw_total / total_s if resident else None,
             "wall_seconds_including_synthesis": wall_s,
             "features_on_rank0_gb": total * 24.304e6 / 1e9,
-            "all_ranks_match": bool(big_ok),
-            "note": ("recordings resident in HBM before the timed region" if resident else
+            "all_ranks_match": bool(big_ok), "ranks_checked": world,
+            "note": ("recordings resident in HBM before the timed region; cohort.run_cohort = kernels per chunk + PSD-only "
+                     "point-to-point gather + DE rebuilt on rank 0" if resident else
                      "180 GB of recordings do not fit one GPU: synthesised chunk by chunk inside the loop, so only the "
-                     "kernels are timed (CUDA events per chunk); there is no gather at 1 GPU")}
-        del big_de, big_psd
+                     "kernels are timed (one CUDA event pair per launch); there is no gather at 1 GPU")}
+        del big_de, big_psd, out_big
 
     if rank == 0:
         peak, peak_src = measured_peaks()

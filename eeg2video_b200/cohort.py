@@ -49,10 +49,10 @@ def _distributed(group):
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
-def gather_to_rank0(local, n_total, group=None, dst=0):
+def gather_to_rank0(local, n_total, group=None, dst=0, out=None):
     """Gather per-rank tensors (leading axis = that rank's subjects, in shard order) into one tensor of
     `n_total` leading entries on rank `dst`.  Returns the full tensor on `dst`, None elsewhere.
-    Uneven shards are handled (sizes follow shard_bounds)."""
+    Uneven shards are handled (sizes follow shard_bounds).  `out`: preallocated destination on `dst`."""
     if not _distributed(group):
         return local
     world = dist.get_world_size(group)
@@ -62,7 +62,8 @@ def gather_to_rank0(local, n_total, group=None, dst=0):
         raise ValueError(f"rank {rank}: expected {sizes[rank]} leading entries, got {local.shape[0]}")
     local = local.contiguous()
     if rank == dst:
-        full = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        full = out if out is not None else torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype,
+                                                       device=local.device)
         parts = list(full.split(sizes, dim=0))
         if all(s == sizes[0] for s in sizes):
             dist.gather(local, gather_list=parts, dst=dst, group=group)
@@ -114,7 +115,7 @@ def process_shard(raw, mode="500ms", chunk_subjects=None, compute=None):
 
 
 def run_cohort(n_local, loader, n_subjects_total, mode="500ms", chunk_subjects=None, group=None, compute=None,
-               rebuild_de=None, dst=0):
+               rebuild_de=None, dst=0, out=None):
     """Shard-local compute, chunk by chunk, + PSD-only point-to-point gather + DE rebuilt on rank `dst`.
 
     loader(lo, hi) -> raw recordings (hi - lo, 7, ch, T) of this rank's LOCAL subjects lo..hi-1 on this rank's device
@@ -123,6 +124,7 @@ def run_cohort(n_local, loader, n_subjects_total, mode="500ms", chunk_subjects=N
     Returns (de, psd) for the whole cohort on rank `dst`, (None, None) elsewhere.  Every rank must call it with the
     same n_subjects_total and chunk_subjects; n_local must equal this rank's shard size (shard_bounds).
     rebuild_de(psd, de): fills `de` from `psd` (default: ops.de_from_psd_; CPU tests pass a stand-in).
+    out: (de, psd) preallocated cohort tensors on rank `dst` (a pipeline that runs cohort after cohort reuses them).
     """
     fn = compute or _default_compute(mode)
     distributed = _distributed(group)
@@ -148,7 +150,7 @@ def run_cohort(n_local, loader, n_subjects_total, mode="500ms", chunk_subjects=N
             q.wait()
         return None, None
 
-    full_de = full_psd = None
+    full_de, full_psd = out if out is not None else (None, None)
     pending = []                                               # [(requests, [(lo, hi) global subject ranges])]
 
     def finish(entry):
@@ -194,7 +196,7 @@ def run_cohort(n_local, loader, n_subjects_total, mode="500ms", chunk_subjects=N
 
 
 def process_cohort(raw_local, n_subjects_total, mode="500ms", chunk_subjects=None, group=None, compute=None,
-                   overlap=False, gather="psd", rebuild_de=None):
+                   overlap=False, gather="psd", rebuild_de=None, out=None):
     """Shard-local compute + gather to rank 0.  Returns (de, psd) for the whole cohort on rank 0, (None, None)
     elsewhere.
 
@@ -206,7 +208,7 @@ def process_cohort(raw_local, n_subjects_total, mode="500ms", chunk_subjects=Non
     """
     if gather == "psd":
         return run_cohort(raw_local.shape[0], lambda lo, hi: raw_local[lo:hi], n_subjects_total, mode, chunk_subjects,
-                          group, compute, rebuild_de)
+                          group, compute, rebuild_de, out=out)
     if gather != "both":
         raise ValueError("gather must be 'psd' or 'both'")
     if overlap and _distributed(group) and chunk_subjects:
@@ -215,8 +217,8 @@ def process_cohort(raw_local, n_subjects_total, mode="500ms", chunk_subjects=Non
         if all(s == sizes[0] for s in sizes) and sizes[0] > 0:
             return _process_cohort_overlapped(raw_local, sizes[0], world, rank, mode, chunk_subjects, group, compute)
     de, psd = process_shard(raw_local, mode, chunk_subjects, compute)
-    de_all = gather_to_rank0(de, n_subjects_total, group)
-    psd_all = gather_to_rank0(psd, n_subjects_total, group)
+    de_all = gather_to_rank0(de, n_subjects_total, group, out=None if out is None else out[0])
+    psd_all = gather_to_rank0(psd, n_subjects_total, group, out=None if out is None else out[1])
     return de_all, psd_all
 
 
