@@ -10,6 +10,7 @@ MODE_500MS, MODE_1S, MODE_2S = 0, 1, 2
 STATUS_ZERO_POWER = 1
 DTYPE_F32, DTYPE_F64, DTYPE_F16, DTYPE_I16 = 0, 1, 2, 3
 EINVAL, ERANGE, EDTYPE = -1, -2, -3
+WINDOWS_WINDOW_MAJOR, WINDOWS_LAST = 0, 1
 
 _i64, _int, _ptr = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
 
@@ -29,6 +30,7 @@ SIGNATURES = {
     "eegfe_de_psd_windows": (_int, [_ptr, _i64, _int, _i64, _ptr, _ptr, _ptr, _ptr]),
     "eegfe_segment_clips": (_int, [_ptr, _int, _i64, _int, _i64, _i64, _i64, _int, _ptr, _ptr]),
     "eegfe_sliding_windows": (_int, [_ptr, _int, _i64, _int, _ptr, _ptr]),
+    "eegfe_sliding_windows_layout": (_int, [_ptr, _int, _i64, _int, _int, _ptr, _ptr]),
     "eegfe_select_units": (_int, [_ptr, _i64, _int, _int, _ptr, _i64, _int, _ptr, _ptr]),
     "eegfe_column_stats_workspace": (_i64, [_i64, _i64, _int]),
     "eegfe_column_stats": (_int, [_ptr, _i64, _i64, _int, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),

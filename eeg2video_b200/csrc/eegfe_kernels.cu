@@ -583,6 +583,24 @@ __global__ void __launch_bounds__(256) sliding_windows_kernel(const unsigned cha
   }
 }
 
+// clips [n_clips][n_ch][400] -> [n_clips][n_ch][100][7]: element (clip, ch, t, w) = clip sample 50 w + t -- the layout the
+// Seq2Seq trainer stacks inline (EEG2Video_New/Seq2Seq/my_autoregressive_transformer.py:309-314, torch.stack(.., dim=-1)).
+// One thread per output element: writes are coalesced, the reads of a warp stay inside one 1600-byte row.
+template <class T>
+__global__ void __launch_bounds__(256) sliding_windows_last_kernel(const T* __restrict__ clips, T* __restrict__ out,
+                                                                    long long n_rows)
+{
+  const long long total = n_rows * 700;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / 700;
+    const int e = static_cast<int>(i - row * 700);
+    const int t = e / 7;
+    const int w = e - t * 7;
+    out[i] = clips[row * 400 + 50 * w + t];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // per-channel statistics of the clip samples (training-split normalisation of the GLMNet raw branch)
 // ---------------------------------------------------------------------------------------------------------------
@@ -1178,6 +1196,29 @@ int eegfe_sliding_windows(const void* clips, int dtype, int64_t n_clips, int n_c
   if (es >= 4 && base_ok) sliding_windows_kernel<8><<<grid, threads, 0, s>>>(src, dst, n_clips, n_ch, es);
   else if (es >= 4 || base_ok) sliding_windows_kernel<4><<<grid, threads, 0, s>>>(src, dst, n_clips, n_ch, es);
   else sliding_windows_kernel<2><<<grid, threads, 0, s>>>(src, dst, n_clips, n_ch, es);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+int eegfe_sliding_windows_layout(const void* clips, int dtype, int64_t n_clips, int n_ch, int layout, void* windows,
+                                 void* stream)
+{
+  if (layout == EEGFE_WINDOWS_WINDOW_MAJOR) return eegfe_sliding_windows(clips, dtype, n_clips, n_ch, windows, stream);
+  if (layout != EEGFE_WINDOWS_LAST) return EEGFE_EINVAL;
+  const int es = esize_of(dtype);
+  if (es == 0) return EEGFE_EDTYPE;
+  if (n_clips < 0 || n_ch <= 0) return EEGFE_EINVAL;
+  if (n_clips == 0) return 0;
+  if (clips == nullptr || windows == nullptr) return EEGFE_EINVAL;
+  const long long n_rows = n_clips * n_ch;
+  const int grid = sm_count() * 8;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (es == 8)
+    sliding_windows_last_kernel<uint64_t><<<grid, 256, 0, s>>>(static_cast<const uint64_t*>(clips), static_cast<uint64_t*>(windows), n_rows);
+  else if (es == 4)
+    sliding_windows_last_kernel<uint32_t><<<grid, 256, 0, s>>>(static_cast<const uint32_t*>(clips), static_cast<uint32_t*>(windows), n_rows);
+  else
+    sliding_windows_last_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(clips), static_cast<uint16_t*>(windows), n_rows);
   ++g_launches;
   return static_cast<int>(cudaGetLastError());
 }

@@ -88,9 +88,16 @@ def segment_clips(raw, fs=200):
     return clips.reshape(tuple(lead) + (CONCEPTS_PER_BLOCK, REPS_PER_CONCEPT, raw.shape[-2], 2 * int(fs)))
 
 
-def sliding_windows(clips):
-    """(..., ch, 400) -> (..., 7, ch, 100): seg_sliding_window(data, 0.5, 0.25) materialised on the device."""
+def sliding_windows(clips, layout="window_major"):
+    """500 ms windows every 250 ms of (..., ch, 400) clips, materialised on the device (bit-exact gather):
+      layout="window_major": (..., 7, ch, 100) -- seg_sliding_window(data, 0.5, 0.25) (segment_sliding_window.py:19)
+      layout="last":         (..., ch, 100, 7) -- the Seq2Seq trainer's inline loop, torch.stack(windows, dim=-1)
+                             (EEG2Video_New/Seq2Seq/my_autoregressive_transformer.py:309-314)."""
     lead = clips.shape[:-2]
     n_ch = clips.shape[-2]
-    out = ops.sliding_windows(clips.reshape(-1, n_ch, 400).contiguous())
-    return out.reshape(tuple(lead) + (7, n_ch, 100))
+    flat = clips.reshape(-1, n_ch, 400).contiguous()
+    if layout == "window_major":
+        return ops.sliding_windows(flat).reshape(tuple(lead) + (7, n_ch, 100))
+    if layout == "last":
+        return ops.sliding_windows_last(flat).reshape(tuple(lead) + (n_ch, 100, 7))
+    raise ValueError("layout must be 'window_major' or 'last'")

@@ -194,6 +194,27 @@ def _(clips):
     return clips.new_empty((clips.shape[0], 7, clips.shape[1], 100))
 
 
+@torch.library.custom_op("eeg2video::sliding_windows_last", mutates_args=(), device_types="cuda")
+def sliding_windows_last(clips: torch.Tensor) -> torch.Tensor:
+    """clips contiguous (n_clips, n_ch, 400) -> (n_clips, n_ch, 100, 7): the Seq2Seq trainer's window layout
+    (my_autoregressive_transformer.py:309-314), bit-exact gather."""
+    _require_cuda(clips, "clips")
+    if clips.dim() != 3 or clips.shape[2] != 400 or clips.dtype not in _COPY_DTYPES or not clips.is_contiguous():
+        raise ValueError("clips must be contiguous (n_clips, n_ch, 400) float32/float64/float16/int16")
+    n_clips, n_ch, _ = clips.shape
+    with torch.cuda.device(clips.device):
+        out = torch.empty((n_clips, n_ch, 100, 7), dtype=clips.dtype, device=clips.device)
+        _lib.check(_lib.load().eegfe_sliding_windows_layout(
+            clips.data_ptr(), _COPY_DTYPES[clips.dtype], n_clips, n_ch, _lib.WINDOWS_LAST, out.data_ptr(),
+            _stream(clips)))
+    return out
+
+
+@sliding_windows_last.register_fake
+def _(clips):
+    return clips.new_empty((clips.shape[0], clips.shape[1], 100, 7))
+
+
 @torch.library.custom_op("eeg2video::glmnet_inputs_from_raw", mutates_args=(), device_types="cuda")
 def glmnet_inputs_from_raw(raw: torch.Tensor, ch_scale: torch.Tensor, ch_shift: torch.Tensor
                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:

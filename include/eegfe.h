@@ -155,6 +155,18 @@ int eegfe_segment_clips(const void* raw, int dtype, int64_t n_blocks, int n_ch, 
 int eegfe_sliding_windows(const void* clips, int dtype, int64_t n_clips, int n_ch, void* windows, void* stream);
 
 /*
+ * The same windows in either on-disk / in-memory layout the reference uses:
+ *   EEGFE_WINDOWS_WINDOW_MAJOR  [n_clips][7][n_ch][100]   seg_sliding_window (segment_sliding_window.py:19)
+ *   EEGFE_WINDOWS_LAST          [n_clips][n_ch][100][7]   the Seq2Seq trainer's inline loop, torch.stack(.., dim=-1)
+ *                                                          (EEG2Video_New/Seq2Seq/my_autoregressive_transformer.py:309-314)
+ * Byte-exact, any 2/4/8-byte element type.
+ */
+#define EEGFE_WINDOWS_WINDOW_MAJOR 0
+#define EEGFE_WINDOWS_LAST 1
+int eegfe_sliding_windows_layout(const void* clips, int dtype, int64_t n_clips, int n_ch, int layout, void* windows,
+                                 void* stream);
+
+/*
  * NEXT ROWS: the first thing every consumer of the feature files does.
  *
  * eegfe_select_units -- pick and re-order clips ("units" of [n_windows][n_cols] floats, n_cols = n_ch * 5), optionally

@@ -20,5 +20,5 @@ from .de_psd import (  # noqa: F401
     extract_de_psd_raw, extract_de_psd_1s, extract_de_psd_sw,
 )
 from .segment import (  # noqa: F401
-    FS, clip_start, extract_2s_segment, segment_subject, seg_sliding_window,
+    FS, clip_start, extract_2s_segment, segment_subject, seg_sliding_window, seq2seq_windows,
 )

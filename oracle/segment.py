@@ -55,3 +55,13 @@ def seg_sliding_window(data, win_s, step_s, fs=200):
     for w, s in enumerate(starts):
         out[:, :, :, w] = data[..., s:s + win]
     return out
+
+
+def seq2seq_windows(clips, window_size=100, overlap=50):
+    """EEG2Video_New/Seq2Seq/my_autoregressive_transformer.py:309-314, the trainer's inline sliding window:
+    EEG = stack([x[..., i:i + window_size] for i in range(0, T - window_size + 1, window_size - overlap)], axis=-1),
+    i.e. (..., ch, 400) -> (..., ch, 100, 7) with the window index LAST."""
+    clips = np.asarray(clips)
+    pieces = [clips[..., i:i + window_size]
+              for i in range(0, clips.shape[-1] - window_size + 1, window_size - overlap)]
+    return np.stack(pieces, axis=-1)

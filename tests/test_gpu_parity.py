@@ -191,6 +191,23 @@ def test_sliding_windows_materialised_bit_exact():
 
 
 # ---- the fused path from raw recordings --------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", (np.float32, np.float64, np.int16))
+def test_seq2seq_window_layout_bit_exact(golden, dtype):
+    """(.., ch, 400) -> (.., ch, 100, 7), the Seq2Seq trainer's layout (my_autoregressive_transformer.py:309-314):
+    bit-exact against the golden made by the reference's own lines and against the oracle on a bigger tensor."""
+    g = golden("seq2seq_golden.npz")
+    got = frontend.sliding_windows(torch.from_numpy(g["codes"].astype(dtype)).to(DEV), layout="last")
+    assert tuple(got.shape) == (2, 3, 5, 100, 7)
+    assert np.array_equal(got.cpu().numpy(), g["windows"].astype(dtype))
+    rng = np.random.default_rng(11)
+    clips = rng.integers(-30000, 30000, (3, 7, 5, 62, 400)).astype(dtype)
+    got = frontend.sliding_windows(torch.from_numpy(clips).to(DEV), layout="last").cpu().numpy()
+    assert np.array_equal(got, oracle.seq2seq_windows(clips))
+    # same bytes as the window-major form, axes permuted
+    major = frontend.sliding_windows(torch.from_numpy(clips).to(DEV)).cpu().numpy()          # (.., 7, 62, 100)
+    assert np.array_equal(np.moveaxis(major, -3, -1), got)
+
+
 @pytest.fixture(scope="module")
 def subject():
     raw = synth.synth_subject(1, device=DEV)

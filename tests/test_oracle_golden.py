@@ -122,3 +122,15 @@ def test_one_second_script_golden(golden):
     clips = decode(g["clips_codes"])                      # (n, 62, 400)
     de, psd = oracle.extract_de_psd_1s(clips[None, None], 200, closed=False)
     assert np.array_equal(de[0, 0], g["de"]) and np.array_equal(psd[0, 0], g["psd"])
+
+
+def test_seq2seq_window_layout_golden(golden):
+    """oracle.seq2seq_windows against the output of the reference's own lines
+    (my_autoregressive_transformer.py:309-314, executed by tests/golden/make_golden_seq2seq.py)."""
+    g = golden("seq2seq_golden.npz")
+    got = oracle.seq2seq_windows(g["codes"].astype(np.float32))
+    assert got.shape == (2, 3, 5, 100, 7)
+    assert np.array_equal(got, g["windows"].astype(np.float32))
+    # the same windows as seg_sliding_window (window axis before the channel axis there, last here)
+    sw = oracle.seg_sliding_window(g["codes"][None].astype(np.float32), 0.5, 0.25)[0]       # (2, 3, 7, 5, 100)
+    assert np.array_equal(np.moveaxis(sw, 2, -1), got)

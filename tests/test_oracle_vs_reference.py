@@ -43,3 +43,19 @@ def test_drivers_live(reference):
     de_ref, psd_ref = reference["extract_DE_PSD_features_1per500ms"].extract_de_psd_sw(win, 200, 0.5)
     de, psd = oracle.extract_de_psd_sw(win, 200, 0.5, closed=False)
     assert np.array_equal(de, de_ref) and np.array_equal(psd, psd_ref)
+
+
+def test_seq2seq_windows_live(reference):
+    """The Seq2Seq trainer's inline loop, executed from the reference file by line number."""
+    import importlib.util
+    import os
+    import torch
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_seq2seq",
+                                                  os.path.join(here, "golden", "make_golden_seq2seq.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2, 2, 3, 4, 400)).astype(np.float32)
+    ref = mod.reference_windows(torch.from_numpy(x)).numpy()
+    assert np.array_equal(ref, oracle.seq2seq_windows(x))
