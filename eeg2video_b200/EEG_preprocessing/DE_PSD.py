@@ -4,25 +4,27 @@ import numpy as np
 from .. import frontend
 from . import _io
 
-_WINDOW_SECONDS = {100: 0.5, 200: 1, 400: 2}
-
 
 def DE_PSD(data, fre, time_window):
     '''
     compute DE and PSD (same contract as the reference function)
     --------
     input:  data [n*m]          n electrodes, m time points; m must equal int(time_window * fre)
-            fre                 sampling rate (200)
-            time_window         window length in seconds (0.5, 1 or 2)
+            fre                 sampling rate (any positive rate; the drivers use 200)
+            time_window         window length in seconds (any length >= 1 sample; the drivers use 0.5, 1 and 2)
     output: de, psd [n*5]       float64, five bands (delta, theta, alpha, beta, gamma) -- DE FIRST, like the
                                 reference (DE_PSD.py:71)
 
     Hann window of int(time_window*fre) points, 200-point FFT (truncating / zero-padding, DE_PSD.py:58),
-    band means of |X|^2 over bins [0,3] [3,7] [7,13] [13,30] [30,98], de = log2(100 * psd).
-    Raises ValueError on a row-length mismatch (the reference's numpy broadcast error, DE_PSD.py:57) and
-    ValueError("math domain error") when a band has zero power (DE_PSD.py:68).
+    band means of |X|^2 over bins range(int(f0 / fre * 200) - 1, int(f1 / fre * 200)) (DE_PSD.py:35-39, :63) --
+    [0,3] [3,7] [7,13] [13,30] [30,98] at 200 Hz --, de = log2(100 * psd).  The three driver shapes (200 Hz; 100,
+    200, 400 samples) run on the fused kernels, everything else on the general kernel (eegfe_de_psd_generic).
+    Raises ValueError on a row-length mismatch (the reference's numpy broadcast error, DE_PSD.py:57),
+    ValueError("math domain error") when a band has zero power (DE_PSD.py:68) and IndexError when a band reaches bin
+    100 (fre < 198: the reference indexes past its 100 magnitudes, DE_PSD.py:64).
     '''
-    _io.check_fs(fre, "fre")
+    if not fre > 0:
+        raise ValueError(f"fre must be positive, got {fre!r}")
     like_torch = _io.is_torch(data)
     if data.ndim != 2:
         raise ValueError("data must be 2-D (electrodes, time points)")
@@ -30,8 +32,8 @@ def DE_PSD(data, fre, time_window):
     if data.shape[1] != length:
         raise ValueError(
             f"operands could not be broadcast together with shapes ({data.shape[1]},) ({length},) ")
-    if length not in _WINDOW_SECONDS:
-        raise NotImplementedError(f"time_window={time_window!r}: supported window lengths are 0.5, 1 and 2 s")
+    if length < 1:
+        raise ValueError(f"time_window * fre = {time_window * fre!r}: the window holds no sample")
     x = _io.to_device_f32(data)
-    de, psd = frontend.de_psd_windows(x, check=True)
+    de, psd = frontend.de_psd_windows(x, check=True, fre=fre)
     return _io.finish((de, psd), like_torch, np.float64)

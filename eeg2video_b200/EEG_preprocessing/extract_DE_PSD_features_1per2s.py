@@ -13,12 +13,15 @@ fre = 200
 
 def extract_de_psd_raw(raw, fs=200):
     """(B, C, R, ch, 400) -> (DE, PSD), each (B, C, R, ch, 5) float32 (reference :16-28)."""
-    _io.check_fs(fs)
     if raw.ndim != 5:
         raise ValueError("raw must be (blocks, concepts, repetitions, channels, samples)")
     if raw.shape[4] != 2 * fre:
         raise ValueError(f"cannot reshape array of size {raw.shape[3] * raw.shape[4]} into shape "
                          f"({raw.shape[3]},{2 * fre})")                 # the reference's reshape error (:23)
+    if int(2 * fs) != 2 * fre:
+        # the reference reshapes with the module constant (:23) but windows with `fs` (:24): any other rate ends in
+        # numpy's broadcast error inside DE_PSD (DE_PSD.py:57)
+        raise ValueError(f"operands could not be broadcast together with shapes ({2 * fre},) ({int(2 * fs)},) ")
     like_torch = _io.is_torch(raw)
     de, psd = frontend.de_psd_from_clips(_io.to_device_f32(raw), "2s", check=True)
     return _io.finish((de, psd), like_torch, np.float32)

@@ -29,20 +29,20 @@ def _clips_behind_window_view(raw):
 
 def extract_de_psd_sw(raw, fs, win_sec):
     """(B, C, R, W, ch, L) windows -> (DE, PSD), each (B, C, R, W, ch, 5) float32 (reference :12-29)."""
-    _io.check_fs(fs)
+    if not fs > 0:
+        raise ValueError(f"fs must be positive, got {fs!r}")
     if raw.ndim != 6:
         raise ValueError("raw must be (blocks, concepts, repetitions, windows, channels, samples)")
     length = int(win_sec * fs)
-    if raw.shape[5] != length:
+    if raw.shape[5] != length or length < 1:
         raise ValueError(f"operands could not be broadcast together with shapes ({raw.shape[5]},) ({length},) ")
-    if length not in (100, 200, 400):
-        raise NotImplementedError(f"win_sec={win_sec!r}: supported window lengths are 0.5, 1 and 2 s")
     like_torch = _io.is_torch(raw)
-    clips = _clips_behind_window_view(raw) if length == 100 else None
+    clips = _clips_behind_window_view(raw) if (length == 100 and fs == 200) else None
     if clips is not None:
         de, psd = frontend.de_psd_from_clips(_io.to_device_f32(clips), "500ms", check=True)
     else:
-        de, psd = frontend.de_psd_windows(_io.to_device_f32(raw), check=True)
+        # any other (fs, win_sec) the reference's DE_PSD accepts: the general kernel behind de_psd_windows
+        de, psd = frontend.de_psd_windows(_io.to_device_f32(raw), check=True, fre=fs)
     return _io.finish((de, psd), like_torch, np.float32)
 
 

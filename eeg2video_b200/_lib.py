@@ -24,6 +24,8 @@ SIGNATURES = {
     "eegfe_glmnet_inputs_from_raw": (_int, [_ptr, _i64, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                             _ptr]),
     "eegfe_channel_stats": (_int, [_ptr, _i64, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "eegfe_de_psd_generic": (_int, [_ptr, _i64, _int, _i64, _ptr, ctypes.POINTER(_int), ctypes.POINTER(_int), _ptr, _ptr,
+                                    _ptr, _ptr]),
     "eegfe_de_from_psd": (_int, [_ptr, _i64, _ptr, _ptr, _ptr]),
     "eegfe_copy2d_async": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "eegfe_de_psd_from_clips": (_int, [_ptr, _i64, _int, _int, _ptr, _ptr, _ptr, _ptr]),

@@ -662,6 +662,54 @@ __global__ void channel_stats_finish_kernel(const double* __restrict__ partial, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// generic DE_PSD: any window length, any sampling rate (DE_PSD.py:33-39, :49-58) -- the slow, general path
+// ---------------------------------------------------------------------------------------------------------------
+// The reference takes ANY fre / time_window: Hann of L = int(time_window * fre) points, fft(., 200) truncating or
+// zero-padding, bins fStartNum - 1 .. fEndNum - 1 with fNum = int(f / fre * 200) (a start of -1 is Python's "last
+// element": bin 99).  The fused kernels cover the three shapes the drivers use (L = 100 / 200 / 400 at 200 Hz); every
+// other shape runs here: one CTA per row, thread k forms bin k of the 200-point DFT directly from the (<= 200) live
+// weighted samples with a sin/cos table in shared memory -- 20 k FMAs per row instead of 2.4 k, no pruning, fp32.
+struct BandBins {
+  int lo[5], hi[5];     // inclusive bin range per band; lo may be -1 (= bin 99)
+  float inv_count[5];
+};
+
+__global__ void __launch_bounds__(128) de_psd_generic_kernel(const float* __restrict__ x, long long n_rows, int n_live,
+                                                              long long row_stride, const float* __restrict__ hann,
+                                                              BandBins bands, float* __restrict__ de,
+                                                              float* __restrict__ psd, int* status)
+{
+  __shared__ float y[200], tc[200], ts[200], power[100];
+  const int k = threadIdx.x;
+  for (int i = k; i < 200; i += 128) sincospif(static_cast<float>(i) * 0.01f, &ts[i], &tc[i]);   // angle 2 pi i / 200
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    __syncthreads();
+    for (int i = k; i < 200; i += 128) y[i] = i < n_live ? __fmul_rn(x[row * row_stride + i], hann[i]) : 0.0f;
+    __syncthreads();
+    if (k < 100) {
+      float re = 0.0f, im = 0.0f;
+      int idx = 0;
+      for (int n = 0; n < n_live; ++n) {
+        re = fmaf(y[n], tc[idx], re);
+        im = fmaf(y[n], -ts[idx], im);
+        idx += k;
+        if (idx >= 200) idx -= 200;
+      }
+      power[k] = fmaf(re, re, im * im);
+    }
+    __syncthreads();
+    if (k < 5) {
+      float e = 0.0f;
+      for (int b = bands.lo[k]; b <= bands.hi[k]; ++b) e += power[b < 0 ? b + 100 : b];
+      const float p = e * bands.inv_count[k];
+      psd[row * 5 + k] = p;
+      de[row * 5 + k] = __log2f(100.0f * p);
+      if (p == 0.0f && status != nullptr) atomicOr(status, EEGFE_STATUS_ZERO_POWER);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // de = log2(100 psd), elementwise: the SAME device expression the feature kernels use (band_features / store_tile),
 // so a rank that received only PSD over NVLink rebuilds DE bit for bit (cohort gather moves half the bytes).
 // ---------------------------------------------------------------------------------------------------------------
@@ -1138,6 +1186,28 @@ int eegfe_de_psd_windows(const float* x, int64_t n_rows, int win_len, int64_t ro
   if (win_len == 100) return run_units<CfgWin100>(job, n_rows, 1, row_stride, a16, s);
   if (win_len == 200) return run_units<CfgWin200>(job, n_rows, 1, row_stride, a16, s);
   return run_units<CfgTwoSec>(job, n_rows, 1, row_stride, a16, s);   // 400: only samples 0..199 count (DE_PSD.py:58)
+}
+
+int eegfe_de_psd_generic(const float* x, int64_t n_rows, int n_live, int64_t row_stride, const float* hann,
+                         const int* band_lo, const int* band_hi, float* de, float* psd, int* status, void* stream)
+{
+  if (n_rows < 0 || n_live < 1 || n_live > 200 || row_stride < n_live || band_lo == nullptr || band_hi == nullptr)
+    return EEGFE_EINVAL;
+  BandBins bands;
+  for (int b = 0; b < 5; ++b) {
+    if (band_lo[b] < -1 || band_hi[b] > 99 || band_hi[b] < band_lo[b]) return EEGFE_EINVAL;
+    bands.lo[b] = band_lo[b];
+    bands.hi[b] = band_hi[b];
+    bands.inv_count[b] = static_cast<float>(1.0 / static_cast<double>(band_hi[b] - band_lo[b] + 1));
+  }
+  if (n_rows == 0) return 0;
+  if (x == nullptr || hann == nullptr || de == nullptr || psd == nullptr) return EEGFE_EINVAL;
+  long long grid = static_cast<long long>(sm_count()) * 16;
+  if (grid > n_rows) grid = n_rows;
+  de_psd_generic_kernel<<<static_cast<unsigned>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n_rows, n_live, row_stride, hann, bands, de, psd, status);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
 }
 
 int eegfe_segment_clips(const void* raw, int dtype, int64_t n_blocks, int n_ch, int64_t block_len,

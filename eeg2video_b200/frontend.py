@@ -67,14 +67,18 @@ def de_psd_from_clips(clips, mode="500ms", check=True):
     return de.reshape(shape), psd.reshape(shape)
 
 
-def de_psd_windows(x, check=True):
-    """DE/PSD of pre-cut windows: float32 CUDA (..., L), L in {100, 200, 400} -> (..., 5)."""
+def de_psd_windows(x, check=True, fre=200):
+    """DE/PSD of pre-cut windows: float32 CUDA (..., L) -> (..., 5).  L in {100, 200, 400} at 200 Hz run on the fused
+    kernels; any other window length / sampling rate on the general kernel (ops.de_psd_generic)."""
     length = x.shape[-1]
     lead = x.shape[:-1]
     flat = x.reshape(-1, length)
     if flat.stride(-1) != 1:
         flat = flat.contiguous()
-    de, psd, status = ops.de_psd_windows(flat)
+    if fre == 200 and length in (100, 200, 400):
+        de, psd, status = ops.de_psd_windows(flat)
+    else:
+        de, psd, status = ops.de_psd_generic(flat, float(fre), int(length))
     if check:
         raise_if_zero_power(status)
     return de.reshape(tuple(lead) + (5,)), psd.reshape(tuple(lead) + (5,))

@@ -155,6 +155,60 @@ def _(x):
     return de, torch.empty_like(de), x.new_empty((1,), dtype=torch.int32)
 
 
+def band_bins(fre):
+    """Inclusive bin ranges of the five bands with the reference's own host expressions (DE_PSD.py:27-29, :35-39, :63):
+    fNum = int(f / fre * 200); bins range(fStartNum - 1, fEndNum).  A start of -1 is Python's "last element" (bin 99);
+    a bin >= 100 is where the reference raises IndexError (magFFTdata has 100 entries, :59)."""
+    lo, hi = [], []
+    for f0, f1 in zip((1, 4, 8, 14, 31), (4, 8, 14, 31, 99)):
+        lo.append(int(f0 / fre * 200) - 1)
+        hi.append(int(f1 / fre * 200) - 1)
+    return lo, hi
+
+
+def hann_weights(length, n_live):
+    """First n_live weights of the reference's Hann window of `length` points (DE_PSD.py:51), float64 -> float32."""
+    import numpy as np
+    n = np.arange(1, n_live + 1, dtype=np.float64)
+    return (0.5 - 0.5 * np.cos(2 * np.pi * n / (length + 1))).astype(np.float32)
+
+
+@torch.library.custom_op("eeg2video::de_psd_generic", mutates_args=(), device_types="cuda")
+def de_psd_generic(x: torch.Tensor, fre: float, window_points: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x float32 (n_rows, L) with L == window_points, unit stride along L; ANY L >= 1 and sampling rate ->
+    de, psd float32 (n_rows, 5).  The general path behind DE_PSD(data, fre, time_window) (DE_PSD.py:8-71)."""
+    import ctypes
+    _require_cuda(x, "x")
+    if x.dim() != 2 or x.dtype != torch.float32 or x.shape[1] != window_points or window_points < 1 or \
+            (x.numel() > 0 and x.stride(1) != 1):
+        raise ValueError("x must be float32 (n_rows, window_points) with unit stride along the window")
+    lo, hi = band_bins(fre)
+    for a, b in zip(lo, hi):
+        if a < -1:
+            raise NotImplementedError(f"fre={fre!r}: band start below bin -1")
+        if b > 99:
+            raise IndexError(f"index {max(a, 100)} is out of bounds for axis 0 with size 100")     # DE_PSD.py:64
+    n_rows, length = x.shape
+    n_live = min(length, 200)
+    row_stride = x.stride(0) if n_rows > 1 else length
+    arr = ctypes.c_int * 5
+    with torch.cuda.device(x.device):
+        hann = torch.from_numpy(hann_weights(length, n_live)).to(x.device)
+        de = torch.empty((n_rows, 5), dtype=torch.float32, device=x.device)
+        psd = torch.empty_like(de)
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.check(_lib.load().eegfe_de_psd_generic(
+            x.data_ptr(), n_rows, n_live, row_stride, hann.data_ptr(), arr(*lo), arr(*hi), de.data_ptr(),
+            psd.data_ptr(), status.data_ptr(), _stream(x)))
+    return de, psd, status
+
+
+@de_psd_generic.register_fake
+def _(x, fre, window_points):
+    de = x.new_empty((x.shape[0], 5), dtype=torch.float32)
+    return de, torch.empty_like(de), x.new_empty((1,), dtype=torch.int32)
+
+
 @torch.library.custom_op("eeg2video::segment_clips", mutates_args=(), device_types="cuda")
 def segment_clips(raw: torch.Tensor, fs: int) -> torch.Tensor:
     """raw (n_blocks, n_ch, T) of a 2/4/8-byte dtype -> clips (n_blocks*200, n_ch, 2*fs), bit-exact gather."""

@@ -19,7 +19,8 @@
  *     band b the value sits at  out[((u * n_windows + w) * n_ch + c) * 5 + b]  -- i.e. the
  *     (block, concept, repetition[, window], channel, band) arrays of the extract_DE_PSD_features_* drivers
  *     with the leading axes flattened.  Bands: delta, theta, alpha, beta, gamma (DE_PSD.py:28-29).
- *   - Sampling rate is fixed at 200 Hz (the only rate the reference's drivers use; FFT length 200, DE_PSD.py:27).
+ *   - The fused kernels are built for 200 Hz and the drivers' three window lengths (FFT length 200, DE_PSD.py:27);
+ *     eegfe_de_psd_generic covers every other (fre, time_window) the reference's DE_PSD accepts.
  */
 #ifndef EEGFE_H_
 #define EEGFE_H_
@@ -197,6 +198,20 @@ int eegfe_column_stats(const float* x, int64_t n_groups, int64_t n_rows, int n_c
                        int64_t group_stride, double* workspace, double* mean, double* var, double* scale, void* stream);
 int eegfe_standardize(const float* x, int64_t n_groups, int64_t n_rows, int n_cols, int64_t row_stride,
                       int64_t group_stride, const double* mean, const double* scale, float* out, void* stream);
+
+/*
+ * Replaces: DE_PSD(data, fre, time_window) for ANY window length and sampling rate (DE_PSD.py:33-39, :49-58) -- the
+ * general, slower path behind the three fused shapes.  The caller (eeg2video_b200/EEG_preprocessing/DE_PSD.py) evaluates
+ * the reference's host expressions and passes their results:
+ *   n_live      = min(L, 200), L = int(time_window * fre): samples of a row that enter fft(., 200) (:58)
+ *   hann        : device float[n_live], 0.5 - 0.5 cos(2 pi (i + 1) / (L + 1)) (:51)
+ *   band_lo/hi  : HOST int[5], inclusive bin range range(fStartNum - 1, fEndNum) with fNum = int(f / fre * 200) (:37-38,
+ *                 :63); band_lo may be -1, which Python reads as the last element, bin 99; hi <= 99
+ *   divisor     = hi - lo + 1 (:66)
+ * x: float32 [n_rows] rows, row_stride elements apart.  de, psd: float32 [n_rows][5].
+ */
+int eegfe_de_psd_generic(const float* x, int64_t n_rows, int n_live, int64_t row_stride, const float* hann,
+                         const int* band_lo, const int* band_hi, float* de, float* psd, int* status, void* stream);
 
 /*
  * DE from PSD, elementwise: de[i] = log2(100 psd[i]) (DE_PSD.py:68) with the device expression of the feature kernels,

@@ -76,6 +76,39 @@ def test_ragged_row_counts(length, n_rows):
     assert_features_close(de, psd, de_ref, psd_ref)
 
 
+@pytest.mark.parametrize("fre,tw", ((200, 0.25), (200, 0.75), (200, 1.5), (200, 3), (200, 0.005), (250, 1), (250, 0.4),
+                                    (256, 0.5), (500, 0.2), (1000, 0.25), (199, 1), (400, 2)))
+def test_de_psd_any_window_length_and_rate(fre, tw):
+    """DE_PSD accepts any window length and sampling rate (DE_PSD.py:33-39, :49-58): Hann of int(tw * fre) points,
+    first 200 samples (zero-padded below), bins from int(f / fre * 200) -- at fre >= 250 the delta band starts at
+    "bin -1", Python's last element (bin 99).  General kernel against the loop-for-loop port of the reference."""
+    length = int(tw * fre)
+    rng = np.random.default_rng(int(fre * 1000 + length))
+    x = (30 * rng.standard_normal((9, length)) + rng.uniform(-20, 20, (9, 1))).astype(np.float32)
+    de, psd = DE_PSD(x, fre, tw)
+    de_ref, psd_ref = oracle.de_psd_loop(x, fre, tw)
+    assert de.shape == (9, 5) and de.dtype == np.float64
+    assert_features_close(de, psd, de_ref, psd_ref)
+
+
+def test_de_psd_low_rates_raise_index_error_like_the_reference():
+    x = np.ones((2, 150), np.float32)
+    with pytest.raises(IndexError, match="out of bounds for axis 0 with size 100"):
+        oracle.de_psd_loop(x + np.arange(150, dtype=np.float32), 150, 1)           # the reference's own failure
+    with pytest.raises(IndexError, match="out of bounds for axis 0 with size 100"):
+        DE_PSD(x, 150, 1)
+
+
+def test_sliding_driver_other_window_lengths():
+    """extract_de_psd_sw(raw, fs, win_sec) for a window the fused kernels do not cover (0.3 s = 60 samples)."""
+    rng = np.random.default_rng(5)
+    raw = (30 * rng.standard_normal((1, 2, 2, 3, 6, 60))).astype(np.float32)
+    de, psd = extract_de_psd_sw(raw, 200, 0.3)
+    de_ref, psd_ref = oracle.extract_de_psd_sw(raw, 200, 0.3, closed=False)
+    assert de.dtype == np.float32 and de.shape == (1, 2, 2, 3, 6, 5)
+    assert_features_close(de, psd, de_ref, psd_ref)
+
+
 def test_zero_power_raises_like_the_reference():
     x = np.ones((4, 200), np.float32)
     x[2] = 0

@@ -78,10 +78,12 @@ def test_window_view_is_recognised_and_unwound():
 def test_shims_validate_before_touching_the_device():
     with pytest.raises(ValueError, match="could not be broadcast"):
         DE_PSD(np.ones((3, 150), np.float32), 200, 1)
-    with pytest.raises(NotImplementedError):
-        DE_PSD(np.ones((3, 250), np.float32), 250, 1)
-    with pytest.raises(NotImplementedError):
-        DE_PSD(np.ones((3, 50), np.float32), 200, 0.25)
+    with pytest.raises(ValueError, match="positive"):
+        DE_PSD(np.ones((3, 250), np.float32), 0, 1)
+    with pytest.raises(ValueError, match="could not be broadcast"):
+        DE_PSD(np.ones((3, 50), np.float32), 250, 0.25)                 # int(0.25 * 250) = 62 samples expected
+    with pytest.raises(ValueError, match="could not be broadcast"):
+        extract_de_psd_raw(np.ones((1, 1, 1, 62, 400), np.float32), fs=250)
     with pytest.raises(ValueError):
         extract_de_psd_raw(np.ones((1, 1, 1, 62, 200), np.float32))
     with pytest.raises(ValueError):
