@@ -510,7 +510,7 @@ def run_gpu_arm(args):
         from eeg2video_b200 import glmnet_inputs
         mean, std = glmnet_inputs.channel_stats(raw, None)
         scale = (1.0 / std).to(torch.float32).contiguous()
-        shift = (-mean / std).to(torch.float32).contiguous()
+        shift = mean.to(torch.float32).contiguous()                         # (x - mean) * (1 / std)
         g_clips = torch.empty((S * 7 * 200, 62, 400), dtype=torch.float32, device=dev)
         g_de = torch.empty((S * 7 * 200, 7, 62, 5), dtype=torch.float32, device=dev)
         g_psd = torch.empty_like(g_de)

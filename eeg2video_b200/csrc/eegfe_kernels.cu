@@ -50,10 +50,10 @@ struct Job {
   long long t_extent;     // valid elements of a channel row (tensor-map bound of the time axis); 0 = unknown
   unsigned tiles_per_clip;  // > 0: tiles never straddle clips (tile = kRows channels of one clip), fetched as tensor boxes
   int rows_tma;             // pre-cut windows in a dense / uniformly strided 2-D array: tile = tensor box of kRows rows
-  // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = x * scale[ch] + shift[ch]
+  // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = (x - mean[ch]) * scale[ch]
   float* norm_out;
   const float* norm_scale;
-  const float* norm_shift;
+  const float* norm_mean;
   long long norm_row0;    // global row index of this launch's first row (rows of earlier launches of a split job)
 };
 
@@ -1078,13 +1078,13 @@ int eegfe_de_psd_from_concepts(const float* x, int64_t n_blocks, int n_ch, int64
 }
 
 int eegfe_glmnet_inputs_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len, int64_t block_stride,
-                                 int64_t ch_stride, const float* ch_scale, const float* ch_shift, float* clips_norm,
+                                 int64_t ch_stride, const float* ch_scale, const float* ch_mean, float* clips_norm,
                                  float* de, float* psd, int* status, void* stream)
 {
   if (n_blocks < 0 || n_ch <= 0) return EEGFE_EINVAL;
   if (n_blocks == 0) return 0;
   if (raw == nullptr || de == nullptr || psd == nullptr || clips_norm == nullptr || ch_scale == nullptr ||
-      ch_shift == nullptr)
+      ch_mean == nullptr)
     return EEGFE_EINVAL;
   if (block_len < 40 * 2600) return EEGFE_ERANGE;
   if (ch_stride < block_len || block_stride < 0) return EEGFE_EINVAL;
@@ -1097,7 +1097,7 @@ int eegfe_glmnet_inputs_from_raw(const float* raw, int64_t n_blocks, int n_ch, i
   job.status = status;
   job.norm_out = clips_norm;
   job.norm_scale = ch_scale;
-  job.norm_shift = ch_shift;
+  job.norm_mean = ch_mean;
   return run_units<CfgSliding500>(job, n_blocks * 200, 200, block_stride, true, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,11 +1,12 @@
 // Streaming form of the fused 500 ms kernel: 16 identical warps per SM, no specialised producer / storer warp.
 //
-// Why.  The ring kernel (de_psd_kernel) runs 2 CTAs x (7 worker warps + 1 producer warp) per SM at 128 registers.
-// Warps land on the four SM sub-partitions round-robin, so three sub-partitions carry 4 worker warps and the
-// fourth carries 2 workers + the 2 producers: the FP32 pipe of that sub-partition idles half of the time and the
-// kernel tops out at 14/16 of the pipe (ncu: 74 %).  A 17th warp does not fit the register file.  Here every warp
-// is a worker (16 x 32 x 128 registers = the whole file) and the two serial duties -- issuing the TMA copies of the
-// next tile, writing a finished tile's features to HBM -- fall to whichever warp happens to finish a tile last.
+// Why.  A warp-specialised ring (de_psd_kernel: worker groups + producer warps, what the 1 s / 2 s modes use) leaves
+// the FP32 pipe of the sub-partitions that host the producer warps partly idle: warps land on the four SM
+// sub-partitions round-robin, and with 16 warps x 128 registers filling the register file a producer warp displaces a
+// worker.  In the first form of this kernel (2 CTAs x (7 workers + 1 producer)) that capped the pipe at 14/16
+// (ncu: 74 %).  Here every warp is a worker (16 x 32 x 128 registers = the whole file) and the two serial duties --
+// issuing the TMA copies of the next tile, writing a finished tile's features to HBM -- fall to whichever warp
+// happens to finish a tile last.
 //
 // Structure.  A CTA owns tiles t = 0, 1, ... (global tile blockIdx.x + t * gridDim.x) of 16 rows; tile t lives in
 // ring slot t % S.  A tile holds 16 rows x 7 windows = 112 channel-windows = 7 HALF-PASSES of 16 lanes (the lane
@@ -128,7 +129,7 @@ __device__ EEGFE_STREAM_DUTY void stream_store_tile(const Job* jobp, const float
 }
 
 // GLMNet raw branch: half-pass q of a tile writes rows q, q + 7, q + 14 of the tile out again as per-channel normalised
-// clips (x * scale[ch] + shift[ch]), 16 lanes x float4 per row -- spread over all passes instead of one warp per tile
+// clips ((x - mean[ch]) * scale[ch]), 16 lanes x float4 per row -- spread over all passes instead of one warp per tile
 // (as a last-reader duty it cost 40 %: 25.6 KB copied by a single warp per tile).
 constexpr int kNormTableChannels = 256;     // per-channel scale / shift cached in shared memory up to this many channels
 __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const float* slot, unsigned row0, int nrows, int q,
@@ -140,7 +141,7 @@ __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const flo
     // (read from global memory, the two factors cost a long-scoreboard stall per row: 20 % of the kernel's stalls)
     const bool cached = job.n_ch <= kNormTableChannels;
     const float sc = cached ? norm_tab[ch] : __ldg(job.norm_scale + ch);
-    const float sh = cached ? norm_tab[kNormTableChannels + ch] : __ldg(job.norm_shift + ch);
+    const float mu = cached ? norm_tab[kNormTableChannels + ch] : __ldg(job.norm_mean + ch);
     const float4* src = reinterpret_cast<const float4*>(slot + r * StreamCfg::kRowStride);
     float4* dst = reinterpret_cast<float4*>(job.norm_out + (job.norm_row0 + grow) * 400);
     float4 v[7];
@@ -150,10 +151,12 @@ __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const flo
 #pragma unroll
     for (int i = 0; i < 7; ++i)
       if (lane16 + 16 * i < 100) {
-        v[i].x = fmaf(v[i].x, sc, sh);
-        v[i].y = fmaf(v[i].y, sc, sh);
-        v[i].z = fmaf(v[i].z, sc, sh);
-        v[i].w = fmaf(v[i].w, sc, sh);
+        // (x - mean) * (1 / std): subtract first -- folded into one FMA (x / std - mean / std) a channel with a large
+        // DC offset would lose the digits the subtraction cancels
+        v[i].x = __fmul_rn(__fsub_rn(v[i].x, mu), sc);
+        v[i].y = __fmul_rn(__fsub_rn(v[i].y, mu), sc);
+        v[i].z = __fmul_rn(__fsub_rn(v[i].z, mu), sc);
+        v[i].w = __fmul_rn(__fsub_rn(v[i].w, mu), sc);
         dst[lane16 + 16 * i] = v[i];
       }
   }
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
     if (job.n_ch <= kNormTableChannels)
       for (unsigned i = threadIdx.x; i < job.n_ch; i += blockDim.x) {
         norm_tab[i] = job.norm_scale[i];
-        norm_tab[kNormTableChannels + i] = job.norm_shift[i];
+        norm_tab[kNormTableChannels + i] = job.norm_mean[i];
       }
   }
 

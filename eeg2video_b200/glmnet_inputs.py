@@ -6,7 +6,8 @@ channel with the training-split mean / std, shaped (N, 1, 62, 400) for the Shall
 in the reference tree, so there is no code to pin against; oracle/glmnet_inputs.py states the arithmetic used here.
 
 On the GPU both products come out of ONE pass over the raw recording: the clip rows staged in shared memory for the
-FFT leave again as normalised clips (kernel template flag NORM of eegfe::de_psd_kernel).
+FFT leave again as normalised clips, (x - mean) * (1 / std) in float32 (kernel template flag NORM of
+eegfe::de_psd_stream_kernel).
 """
 import torch
 
@@ -39,9 +40,11 @@ def build_inputs(raw, mean, std, check=True):
     flat = raw.reshape((-1,) + tuple(raw.shape[-2:]))
     mean64 = torch.as_tensor(mean, dtype=torch.float64, device=flat.device)
     std64 = torch.as_tensor(std, dtype=torch.float64, device=flat.device)
-    scale = (1.0 / std64).to(torch.float32).contiguous()
-    shift = (-mean64 / std64).to(torch.float32).contiguous()
-    clips, de, psd, status = ops.glmnet_inputs_from_raw(flat, scale, shift)
+    # a constant channel (std == 0) keeps scale 1, as scikit-learn's scalers do (sklearn _handle_zeros_in_scale), instead
+    # of turning the whole channel into inf / NaN
+    safe_std = torch.where(std64 == 0, torch.ones_like(std64), std64)
+    scale = (1.0 / safe_std).to(torch.float32).contiguous()
+    clips, de, psd, status = ops.glmnet_inputs_from_raw(flat, scale, mean64.to(torch.float32).contiguous())
     if check:
         frontend.raise_if_zero_power(status)
     return (clips.reshape(tuple(lead) + (40, 5, 1, n_ch, 400)),

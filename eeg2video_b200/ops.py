@@ -270,15 +270,15 @@ def _(clips):
 
 
 @torch.library.custom_op("eeg2video::glmnet_inputs_from_raw", mutates_args=(), device_types="cuda")
-def glmnet_inputs_from_raw(raw: torch.Tensor, ch_scale: torch.Tensor, ch_shift: torch.Tensor
+def glmnet_inputs_from_raw(raw: torch.Tensor, ch_scale: torch.Tensor, ch_mean: torch.Tensor
                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """raw float32 (n_blocks, n_ch, T) + per-channel scale / shift (float32, n_ch) ->
-    clips_norm (n_blocks*200, n_ch, 400), de, psd (n_blocks*200, 7, n_ch, 5), status."""
+    """raw float32 (n_blocks, n_ch, T) + per-channel scale = 1 / std and mean (float32, n_ch) ->
+    clips_norm = (x - mean) * scale (n_blocks*200, n_ch, 400), de, psd (n_blocks*200, 7, n_ch, 5), status."""
     _require_cuda(raw, "raw")
     if raw.dim() != 3 or raw.dtype != torch.float32 or (raw.numel() > 0 and raw.stride(2) != 1):
         raise ValueError("raw must be float32 (n_blocks, n_ch, T) with a contiguous time axis")
     n_blocks, n_ch, t_len = raw.shape
-    for name, v in (("ch_scale", ch_scale), ("ch_shift", ch_shift)):
+    for name, v in (("ch_scale", ch_scale), ("ch_mean", ch_mean)):
         if v.dtype != torch.float32 or v.shape != (n_ch,) or not v.is_contiguous() or v.device != raw.device:
             raise ValueError(f"{name} must be a contiguous float32 ({n_ch},) tensor on {raw.device}")
     with torch.cuda.device(raw.device):
@@ -288,12 +288,12 @@ def glmnet_inputs_from_raw(raw: torch.Tensor, ch_scale: torch.Tensor, ch_shift: 
         status = torch.zeros(1, dtype=torch.int32, device=raw.device)
         _lib.check(_lib.load().eegfe_glmnet_inputs_from_raw(
             raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), ch_scale.data_ptr(),
-            ch_shift.data_ptr(), clips.data_ptr(), de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
+            ch_mean.data_ptr(), clips.data_ptr(), de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
     return clips, de, psd, status
 
 
 @glmnet_inputs_from_raw.register_fake
-def _(raw, ch_scale, ch_shift):
+def _(raw, ch_scale, ch_mean):
     clips = raw.new_empty((raw.shape[0] * 200, raw.shape[1], 400), dtype=torch.float32)
     de = raw.new_empty((raw.shape[0] * 200, 7, raw.shape[1], 5), dtype=torch.float32)
     return clips, de, torch.empty_like(de), raw.new_empty((1,), dtype=torch.int32)

@@ -99,9 +99,10 @@ class HostPipeline:
             raise ValueError("raw_host must be contiguous float32 (features_from_host converts other types)")
         n_blocks = raw_host.shape[0]
         cb = self.chunk_blocks
-        status_all = torch.zeros(1, dtype=torch.int32, device=self.device)
         staged = [None, None]          # events: stage[i] free again (its kernel finished)
         with torch.cuda.device(self.device):
+            with torch.cuda.stream(self.compute):      # zero-filled on the stream that ORs into it (no cross-stream race)
+                status_all = torch.zeros(1, dtype=torch.int32, device=self.device)
             for i, lo in enumerate(range(0, n_blocks, cb)):
                 hi = min(lo + cb, n_blocks)
                 buf = self.stage[i & 1][: hi - lo]

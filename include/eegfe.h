@@ -93,13 +93,14 @@ int eegfe_de_psd_from_concepts(const float* x, int64_t n_blocks, int n_ch, int64
  * split statistics"; model input contracts EEG-VP/models.py:119, :364) but its trainer / inference scripts are not in
  * the tree, so this row has no reference code to pin against (oracle/glmnet_inputs.py states the arithmetic).
  *
- * clips_norm   float32 [n_blocks * 200][n_ch][400] = x * ch_scale[c] + ch_shift[c]   (scale = 1/std, shift = -mean/std);
- *              viewed as (N, 1, n_ch, 400) it is the input of glfnet / shallownet.
+ * clips_norm   float32 [n_blocks * 200][n_ch][400] = (x - ch_mean[c]) * ch_scale[c]   (scale = 1/std; the subtraction
+ *              comes first so that a large DC offset does not cancel digits); viewed as (N, 1, n_ch, 400) it is the
+ *              input of glfnet / shallownet.
  * de, psd      float32 [n_blocks * 200][7][n_ch][5], the 500 ms features (identical to eegfe_de_psd_from_raw).
  * Requires 16-byte aligned rows (block_len, strides multiples of 4 samples) -> EEGFE_EINVAL otherwise.
  */
 int eegfe_glmnet_inputs_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len, int64_t block_stride,
-                                 int64_t ch_stride, const float* ch_scale, const float* ch_shift, float* clips_norm,
+                                 int64_t ch_stride, const float* ch_scale, const float* ch_mean, float* clips_norm,
                                  float* de, float* psd, int* status, void* stream);
 
 /*

@@ -475,6 +475,27 @@ def test_glmnet_channel_stats_and_inputs(subject):
     assert (x.std(dim=(0, 1, 2, 3, 5), unbiased=False) - 1).abs().max() < 1e-5
 
 
+def test_glmnet_inputs_large_offset_and_constant_channel():
+    """(x - mean) * (1 / std) subtracts FIRST: a channel riding on a DC offset 1000x its std keeps its digits; a constant
+    channel (std == 0) comes out as zeros, not inf / NaN (scale 1, scikit-learn's convention)."""
+    from eeg2video_b200 import glmnet_inputs
+    from oracle import glmnet_inputs as oracle_glm
+    raw = synth.synth_blocks(1, 31, device=DEV, channels=16)
+    raw[:, 3] = raw[:, 3] * 0.1 + 30000.0            # std 3, offset 30000
+    raw[:, 5] = 7.5                                  # constant channel
+    mean, std = glmnet_inputs.channel_stats(raw)
+    assert float(std[5]) == 0.0
+    clips, _, _ = glmnet_inputs.build_inputs(raw, mean, std, check=False)
+    got = clips.cpu().numpy()
+    assert np.all(np.isfinite(got)) and np.all(got[..., 5, :] == 0.0)
+    std_np = std.cpu().numpy().copy()
+    std_np[5] = 1.0
+    want = oracle_glm.normalised_clips(raw.cpu().numpy(), mean.cpu().numpy(), std_np)
+    assert np.max(np.abs(got - want)) <= 2e-3 * 1.0 and np.max(np.abs(got[..., 3, :] - want[..., 3, :])) <= 1e-3
+    keep = [c for c in range(16) if c not in (3, 5)]
+    assert np.max(np.abs(got[..., keep, :] - want[..., keep, :])) <= 4e-6
+
+
 def test_glmnet_inputs_need_aligned_rows():
     from eeg2video_b200 import glmnet_inputs
     raw = synth.synth_blocks(1, 3, device=DEV, channels=4, block_len=104001)
