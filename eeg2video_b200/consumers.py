@@ -137,3 +137,35 @@ def classifier_fold_inputs(features, test_block):
     return {"train": StandardScaler().fit_transform(train),
             "test": StandardScaler().fit_transform(per_block[test_block]),
             "val": StandardScaler().fit_transform(per_block[val_block])}
+
+
+class GraphedBuild:
+    """A consumer-side input build captured ONCE as a CUDA graph and replayed with one launch.
+
+    The builds above are chains of small kernels (gather, two statistics passes with their reductions, transform: six
+    launches over a few tens of MB), bound by launch latency rather than by HBM.  `build(*inputs)` is run once to warm
+    up, captured into a torch.cuda.CUDAGraph on a side stream, and `replay()` re-runs the same kernels on the SAME
+    input tensors (refill them in place -- e.g. ``features.copy_(new)`` -- before replaying) into the same outputs.
+
+        idx = torch.from_numpy(clip_index(range(6), gt, labels)).cuda()      # uploads happen before the capture
+        g = GraphedBuild(lambda f: StandardScaler().fit_transform(ops.select_units(f, idx, True)), units)
+        x = g.replay()            # one graph launch; x is overwritten by the next replay
+
+    `build` may hold device work only (kernels, device allocations): host-to-device copies cannot be captured.
+    """
+
+    def __init__(self, build, *inputs):
+        self.inputs = inputs
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            build(*inputs)                                   # warm-up: lazy initialisation happens outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = build(*inputs)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs

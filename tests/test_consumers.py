@@ -178,3 +178,32 @@ def test_gpu_grouped_scaler_equals_per_group():
         assert torch.equal(one.transform(x[g]), y[g])
     with pytest.raises(ValueError, match="group axis"):
         sc.transform(x[0])
+
+
+@pytest.mark.gpu
+def test_gpu_graphed_build_replays_with_new_features(gold):
+    """consumers.GraphedBuild: the six-kernel build captured as one CUDA graph; replay after refilling the input tensor
+    in place must equal the kernel-by-kernel build of the new features, bit for bit."""
+    import torch
+    from eeg2video_b200 import _lib, consumers
+    gt = gold["gt_label"]
+    feat = torch.from_numpy(decode(gold["codes_1s"], np.float32)).cuda()
+    chosen = list(range(1, 41))
+    # the index table is uploaded BEFORE the capture (a host-to-device copy cannot be captured); the captured function
+    # holds device work only: gather + mean over the windows, scaler fit, transform
+    idx = torch.from_numpy(consumers.clip_index(range(6), gt, chosen)).cuda()
+
+    def build(f):
+        x = ops_mod.select_units(f.reshape(7 * 40 * 5, 2, -1), idx, True)
+        return consumers.StandardScaler().fit_transform(x)
+    from eeg2video_b200 import ops as ops_mod
+    graphed = consumers.GraphedBuild(build, feat)
+    want = consumers.semantic_predictor_inputs(feat, gt, chosen)[0]
+    assert torch.equal(graphed.replay(), want)
+    feat.mul_(1.5).add_(0.25)                                    # new features, same buffer
+    want2 = consumers.semantic_predictor_inputs(feat, gt, chosen)[0]
+    before = _lib.launch_count()
+    got2 = graphed.replay()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == before                         # no launch goes through the library: one graph launch
+    assert torch.equal(got2, want2) and not torch.equal(want2, want)
