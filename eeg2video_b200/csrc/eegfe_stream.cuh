@@ -33,6 +33,12 @@ namespace eegfe {
 #ifndef EEGFE_STREAM_WARPS
 #define EEGFE_STREAM_WARPS 16
 #endif
+// 1: every lane stores its own 5 DE + 5 PSD values straight to HBM (no staging tile, no store duty, no `staged` /
+//    `drained` handshake; the staging memory becomes an eighth input slot).  0: the round-1 form (results staged
+//    [window][row][band] per tile, written out by the warp that finishes the tile last).
+#ifndef EEGFE_DIRECT_STORE
+#define EEGFE_DIRECT_STORE 1
+#endif
 template <int ROWS_, int WINDOWS_, int HOP_, int LOAD_, int STRIDE_, int VEC_, int SLOTS_, bool LANEMAP_,
           int WARPS_ = EEGFE_STREAM_WARPS>
 struct StreamCfgT {
@@ -52,20 +58,24 @@ struct StreamCfgT {
   static constexpr int kSlotFloats = kRows * kRowStride;
   static constexpr int kOutFloats = kUnits * 5;            // per staging array
   static constexpr int kSplit = 1;                         // store_tile: staged values are final (de, psd)
-  static constexpr int kSmemBytes = (kSlots * (kSlotFloats + 2 * kOutFloats) + kUnits) * 4;
+  static constexpr bool kDirectStore = EEGFE_DIRECT_STORE != 0;
+  static constexpr int kSmemBytes = (kSlots * (kSlotFloats + (kDirectStore ? 0 : 2 * kOutFloats)) + kUnits) * 4;
   static_assert(kUnits % 16 == 0, "a tile is a whole number of half-passes");
   static_assert(kRowBytes % 16 == 0 && kRowStride % 4 == 0, "TMA bulk copies need 16-byte aligned rows");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
 // 500 ms windows sliding over 2 s clip rows (fused segmentation): 16 rows x 7 windows, LDS.64 + lane map
-using StreamCfg = StreamCfgT<16, 7, 50, 400, 404, 2, 7, true>;
+#ifndef EEGFE_STREAM_SLOTS
+#define EEGFE_STREAM_SLOTS (EEGFE_DIRECT_STORE ? 8 : 7)
+#endif
+using StreamCfg = StreamCfgT<16, 7, 50, 400, 404, 2, EEGFE_STREAM_SLOTS, true>;
 // pre-cut 500 ms windows (the reference's own call pattern, DE_PSD on a materialised (.., 100) array): 64 rows of 100
 // samples, dense rows (LDS.128 over consecutive rows is conflict-free because 100 / 4 = 25 is odd); a tile of
 // contiguous rows arrives with ONE bulk copy.
 #ifndef EEGFE_WIN100_WARPS
 #define EEGFE_WIN100_WARPS 12   // 168 registers, no spills: 11.9 G cw/s against 10.5 G with 16 warps at 128 registers
 #endif
-using StreamCfgWin100 = StreamCfgT<64, 1, 0, 100, 100, 4, 7, false, EEGFE_WIN100_WARPS>;
+using StreamCfgWin100 = StreamCfgT<64, 1, 0, 100, 100, 4, EEGFE_STREAM_SLOTS, false, EEGFE_WIN100_WARPS>;
 
 __constant__ unsigned char c_lane_map_500_r16[112] = {EEGFE_LANE_MAP_500_R16};
 
@@ -170,7 +180,8 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const ring = reinterpret_cast<float*>(smem_raw);                     // [slot][row][kRowStride]
   float* const stage = ring + C::kSlots * C::kSlotFloats;                      // [slot][de | psd][window][row][band]
-  int* const unit_meta = reinterpret_cast<int*>(stage + C::kSlots * 2 * C::kOutFloats);   // [kUnits]
+  int* const unit_meta =
+      reinterpret_cast<int*>(stage + (C::kDirectStore ? 0 : C::kSlots * 2 * C::kOutFloats));         // [kUnits]
   __shared__ uint64_t full_bar[C::kSlots];
   __shared__ unsigned consumed[C::kSlots], staged[C::kSlots], drained[C::kSlots];
   // armed[s] = number of tiles whose copies have been ISSUED into slot s.  A parity wait on full[s] cannot tell
@@ -280,19 +291,38 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
     }
     asm volatile("" : "+r"(pass));                        // everything below is recomputed from `pass` alone
     locate();
-    if (live) {
-      // staging rows of the slot's previous tile must have been written out (true long before, in practice)
-      while (ld_acquire_smem(&drained[s]) < gen) __nanosleep(32);
-      float* const sd = stage + s * 2 * C::kOutFloats + ((meta >> 14) & 0x7ff);
+    if constexpr (C::kDirectStore) {
+      if (live) {
+        // features [clip][window][channel][band]: this lane's ten values go straight out.  The 16 lanes of a half-pass
+        // cover runs of 8 (lane-mapped tiles) or 16 consecutive channels of one window, i.e. 160 / 320 contiguous bytes
+        // per array; the five 4-byte stores of a lane hit the same sectors back to back and merge in L2.
+        const unsigned g = tile_row0(t) + static_cast<unsigned>(meta >> 25);
+        const unsigned u = g / job.n_ch;
+        const unsigned ch = g - u * job.n_ch;
+        const unsigned w = C::kWindows == 1 ? 0u : static_cast<unsigned>((meta >> 14) & 0x7ff) / (5u * C::kRows);
+        const long long o = (static_cast<long long>(u * C::kWindows + w) * job.n_ch + ch) * 5;
 #pragma unroll
-      for (int b = 0; b < 5; ++b) {
-        sd[b] = de[b];
-        sd[C::kOutFloats + b] = psd[b];
+        for (int b = 0; b < 5; ++b) {
+          job.de[o + b] = de[b];
+          job.psd[o + b] = psd[b];
+        }
+      }
+    } else {
+      if (live) {
+        // staging rows of the slot's previous tile must have been written out (true long before, in practice)
+        while (ld_acquire_smem(&drained[s]) < gen) __nanosleep(32);
+        float* const sd = stage + s * 2 * C::kOutFloats + ((meta >> 14) & 0x7ff);
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+          sd[b] = de[b];
+          sd[C::kOutFloats + b] = psd[b];
+        }
       }
     }
     __syncwarp();
     // ---- retire: per tile touched by this pass (one or two), count this warp's half-passes in; whoever completes
-    //      the count refills the input slot, whoever completes the staging count writes the tile out ----
+    //      the count refills the input slot (and, with staged results, whoever completes the staging count writes the
+    //      tile out) ----
     const unsigned h0 = 2 * pass;
     const unsigned t0 = h0 / C::kHalfPasses;
     const unsigned t1 = (h0 + 1 < n_half) ? (h0 + 1) / C::kHalfPasses : t0;
@@ -305,7 +335,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
       unsigned last = 0;
       if (lane == 0) {
         last = (atom_add_acq_rel_smem(&consumed[sk], cnt) + cnt == done) ? 1u : 0u;
-        last |= (atom_add_acq_rel_smem(&staged[sk], cnt) + cnt == done) ? 2u : 0u;
+        if constexpr (!C::kDirectStore) last |= (atom_add_acq_rel_smem(&staged[sk], cnt) + cnt == done) ? 2u : 0u;
       }
       last = __shfl_sync(0xffffffffu, last, 0);
       if (last & 1u) {
@@ -315,10 +345,12 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
                               tile_nrows(r0));
         }
       }
-      if (last & 2u) {
-        const unsigned r0 = tile_row0(tk);
-        stream_store_tile<C>(&job, stage + sk * 2 * C::kOutFloats, r0, tile_nrows(r0));
-        if (lane == 0) st_release_smem(&drained[sk], tk / C::kSlots + 1);
+      if constexpr (!C::kDirectStore) {
+        if (last & 2u) {
+          const unsigned r0 = tile_row0(tk);
+          stream_store_tile<C>(&job, stage + sk * 2 * C::kOutFloats, r0, tile_nrows(r0));
+          if (lane == 0) st_release_smem(&drained[sk], tk / C::kSlots + 1);
+        }
       }
     }
   }
