@@ -48,6 +48,7 @@ struct Job {
   unsigned d1, d2;
   unsigned n_ch;
   long long t_extent;     // valid elements of a channel row (tensor-map bound of the time axis); 0 = unknown
+  int row_align;            // bytes every row start is a multiple of: 16 (TMA bulk copies), else 8 or 4 (cp.async loader)
   unsigned tiles_per_clip;  // > 0: tiles never straddle clips (tile = kRows channels of one clip), fetched as tensor boxes
   int rows_tma;             // pre-cut windows in a dense / uniformly strided 2-D array: tile = tensor box of kRows rows
   // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = (x - mean[ch]) * scale[ch]
@@ -897,7 +898,17 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
   Job job = job_in;
   job.tiles_per_clip = 0;
   job.rows_tma = 0;
+  job.row_align = 16;
   unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
+  if (!aligned16 && job.norm_out == nullptr) {
+    // 100-sample windows: the streaming kernel also takes rows that are only 8- / 4-byte aligned (cp.async loader)
+    const bool even = reinterpret_cast<uintptr_t>(job.in) % 8 == 0 && job.base % 2 == 0 && job.s0 % 2 == 0 &&
+                      job.s1 % 2 == 0 && job.s2 % 2 == 0 && job.ch_stride % 2 == 0;
+    job.row_align = even ? 8 : 4;
+    if constexpr (C::kLoad == 400 && C::kWindows == 7) return launch_stream<StreamCfg>(job, stream);
+    if constexpr (C::kLoad == 100 && C::kWindows == 1) return launch_stream<StreamCfgWin100>(job, stream);
+    job.row_align = 16;
+  }
   if (aligned16) {
     if constexpr (C::kLoad == 400 && C::kWindows == 7) {
       return launch_stream<StreamCfg>(job, stream);        // 500 ms sliding windows: the streaming kernel

@@ -104,14 +104,60 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // constants cannot stay live across a call and are re-materialised every pass); -DEEGFE_STREAM_DUTY=__noinline__
 // builds the out-of-line form for comparison.
 
+// cp.async of BYTES (4 or 8) per lane: rows that are not 16-byte aligned cannot ride on TMA bulk copies
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* dst_smem, const void* src_gmem)
+{
+  if constexpr (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+// the executing thread's earlier cp.async count as one more pending arrival on `bar` until they have landed
+__device__ __forceinline__ void cp_async_track(uint64_t* bar)
+{
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Rows that are only 8- or 4-byte aligned (job.row_align; an odd block length or stride): 8- / 4-byte cp.async
+// (LDGSTS), one row per step, lanes side by side; the barrier phase completes when the issuing warp's copies have landed.
+template <class SC>
+__device__ __noinline__ void stream_load_tile_small(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
+                                                    unsigned generation, unsigned row0, int nrows)
+{
+  const Job& job = *jobp;
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) st_release_smem(armed, generation + 1u);
+#pragma unroll 1
+  for (int r = 0; r < nrows; ++r) {
+    const float* src = job.in + row_offset(job, row0 + r, SC::kWindows, nullptr);
+    float* dst = slot + r * SC::kRowStride;
+    if (job.row_align == 8) {
+#pragma unroll 1
+      for (int i = 2 * lane; i < SC::kLoad; i += 64) cp_async_small<8>(dst + i, src + i);
+    } else {
+#pragma unroll 1
+      for (int i = lane; i < SC::kLoad; i += 32) cp_async_small<4>(dst + i, src + i);
+    }
+  }
+  cp_async_track(bar);                     // every lane: +1 pending arrival until its copies are in shared memory
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);         // the phase's own arrival, after all 32 have been registered
+  __syncwarp();
+}
+
 // whole warp: re-arm `bar` and issue the bulk copies of the tile starting at global row `row0`: one per row, or a
-// single one when the rows sit back to back in HBM exactly as they do in the slot (pre-cut windows, dense array)
+// single one when the rows sit back to back in HBM exactly as they do in the slot (pre-cut windows, dense array).
 template <class SC>
 __device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
                                                    unsigned generation, unsigned row0, int nrows)
 {
   const Job& job = *jobp;
   const int lane = threadIdx.x & 31;
+  if (job.row_align < 16) {                  // cold path, kept out of line: the hot loop stays inside the instruction cache
+    stream_load_tile_small<SC>(jobp, slot, bar, armed, generation, row0, nrows);
+    return;
+  }
   fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy refill
   if (lane == 0) {
     mbar_arrive_expect_tx(bar, nrows * SC::kRowBytes);

@@ -51,14 +51,16 @@ def de_psd_from_raw(raw: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.T
         psd = torch.empty_like(de)
         status = torch.zeros(1, dtype=torch.int32, device=raw.device)
         aligned = raw.data_ptr() % 16 == 0 and raw.stride(0) % 4 == 0 and raw.stride(1) % 4 == 0
-        if aligned or n_blocks == 0 or t_len < 40 * 2600:
+        # 500 ms mode: the streaming kernel fetches rows of any alignment itself (TMA bulk copies, else 8- / 4-byte cp.async)
+        if aligned or mode == _lib.MODE_500MS or n_blocks == 0 or t_len < 40 * 2600:
             _lib.check(lib.eegfe_de_psd_from_raw(
                 raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), mode,
                 de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
         else:
-            # Rows that are only 4-byte aligned (odd block length / strides) cannot be fetched by TMA bulk copies.
-            # Re-align them with the byte-exact clip gather (one extra HBM pass through a bounded scratch buffer) and
-            # run the fast kernels on that; libeegfe's own no-workspace fallback for such rows is 2-60x slower.
+            # 1 s / 2 s modes: rows that are only 4-byte aligned (odd block length / strides) cannot be fetched by the
+            # ring kernel's TMA bulk copies.  Re-align them with the byte-exact clip gather (one extra HBM pass through a
+            # bounded scratch buffer) and run the fast kernels on that; libeegfe's own no-workspace fallback for such
+            # rows is 2-60x slower.
             chunk = max(1, min(n_blocks, 28))
             scratch = torch.empty((chunk * 200, n_ch, 400), dtype=torch.float32, device=raw.device)
             for lo in range(0, n_blocks, chunk):

@@ -162,3 +162,24 @@ def test_preprocess_all_shards_recordings_by_rank():
     assert preprocess_all.shard_for_this_rank(names, {}) == names
     with pytest.raises(ValueError):
         preprocess_all.shard_for_this_rank(names, {"WORLD_SIZE": "2", "RANK": "2"})
+
+
+def test_band_bins_and_hann_follow_the_reference_expressions():
+    """The host expressions handed to the general kernel (ops.band_bins, ops.hann_weights) against the oracle's
+    restatement of DE_PSD.py:35-39, :51, :63 over a sweep of sampling rates and window lengths."""
+    from hypothesis import given, settings, strategies as st
+    from eeg2video_b200 import ops
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.one_of(st.integers(100, 4000), st.floats(100.0, 4000.0, allow_nan=False)))
+    def bins(fre):
+        lo, hi = ops.band_bins(fre)
+        assert list(zip(lo, hi)) == oracle.band_bin_ranges(fre)
+    bins()
+    assert ops.band_bins(200) == ([0, 3, 7, 13, 30], [3, 7, 13, 30, 98])
+    assert ops.band_bins(250)[0][0] == -1                        # "bin -1": Python's last element, bin 99
+    assert max(ops.band_bins(150)[1]) >= 100                     # where the reference raises IndexError
+    for length in (1, 7, 100, 199, 200, 201, 640):
+        n_live = min(length, 200)
+        want = oracle.hann_window(length)[:n_live].astype(np.float32)
+        assert np.array_equal(ops.hann_weights(length, n_live), want)
