@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   const int lane = tid & 31;
   // Tiles: kRows consecutive rows -- or, with job.tiles_per_clip (tensor-copy producer), kRows consecutive CHANNELS
   // of one clip, so that a tile is a rectangle of the (time, channel, block) tensor; a clip's last tile is short.
-  constexpr bool kTensorLoads = (C::kLoad == 200);       // rows that fit one tensor box (inner extent <= 256)
+  // rows that fit one tensor box (inner extent <= 256); compiled into the 2 s instantiation only (measurement option)
+  constexpr bool kTensorLoads = (C::kLoad == 200 && C::kHann == kHannTwoSec);
   const unsigned tpc = kTensorLoads ? job.tiles_per_clip : 0u;
   const unsigned n_tiles = tpc ? (job.total_rows / job.n_ch) * tpc : (job.total_rows + C::kRows - 1) / C::kRows;
   // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -390,6 +391,28 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
           st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
           tma_load_box(ring + s * C::kSlotFloats, &job.map, x, y, z, &full_bar[s]);
         }
+        __syncwarp();
+        continue;
+      }
+      if (job.row_align < 16) {
+        // rows that are only 8- / 4-byte aligned (odd block length or stride): cp.async instead of TMA bulk copies, one
+        // row per step, lanes side by side; the phase completes when this warp's copies have landed
+        if (lane == 0) st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
+#pragma unroll 1
+        for (unsigned r = 0; r < nrows; ++r) {
+          const float* src = job.in + row_offset(job, row0 + r, C::kWindows, nullptr);
+          float* dst = ring + s * C::kSlotFloats + r * C::kRowStride;
+          if (job.row_align == 8) {
+#pragma unroll 1
+            for (int i = 2 * lane; i < C::kLoad; i += 64) cp_async_small<8>(dst + i, src + i);
+          } else {
+#pragma unroll 1
+            for (int i = lane; i < C::kLoad; i += 32) cp_async_small<4>(dst + i, src + i);
+          }
+        }
+        cp_async_track(&full_bar[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
         __syncwarp();
         continue;
       }
@@ -901,13 +924,11 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
   job.row_align = 16;
   unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (!aligned16 && job.norm_out == nullptr) {
-    // 100-sample windows: the streaming kernel also takes rows that are only 8- / 4-byte aligned (cp.async loader)
+    // rows that are only 8- / 4-byte aligned: the same kernels with their cp.async loader instead of TMA bulk copies
     const bool even = reinterpret_cast<uintptr_t>(job.in) % 8 == 0 && job.base % 2 == 0 && job.s0 % 2 == 0 &&
                       job.s1 % 2 == 0 && job.s2 % 2 == 0 && job.ch_stride % 2 == 0;
     job.row_align = even ? 8 : 4;
-    if constexpr (C::kLoad == 400 && C::kWindows == 7) return launch_stream<StreamCfg>(job, stream);
-    if constexpr (C::kLoad == 100 && C::kWindows == 1) return launch_stream<StreamCfgWin100>(job, stream);
-    job.row_align = 16;
+    aligned16 = true;                        // same kernels as aligned rows, loader switched by job.row_align
   }
   if (aligned16) {
     if constexpr (C::kLoad == 400 && C::kWindows == 7) {
@@ -916,9 +937,9 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
       return launch_stream<StreamCfgWin100>(job, stream);  // pre-cut 500 ms windows: the streaming kernel, dense rows
     } else {
       if (job.norm_out != nullptr) return EEGFE_EINVAL;
-      if constexpr (C::kLoad == 200) {
+      if constexpr (C::kLoad == 200 && C::kHann == kHannTwoSec) {
         // 200-sample rows at a 204-float pitch are one tensor box per tile
-        if (attach_tensor_map<C>(job)) {
+        if (job.row_align == 16 && attach_tensor_map<C>(job)) {
           ++g_tma_launches;
           if (job.tiles_per_clip) n_tiles = (job.total_rows / job.n_ch) * job.tiles_per_clip;
         }

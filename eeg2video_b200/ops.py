@@ -50,27 +50,11 @@ def de_psd_from_raw(raw: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.T
         de = torch.empty((n_blocks * 200, n_win, n_ch, 5), dtype=torch.float32, device=raw.device)
         psd = torch.empty_like(de)
         status = torch.zeros(1, dtype=torch.int32, device=raw.device)
-        aligned = raw.data_ptr() % 16 == 0 and raw.stride(0) % 4 == 0 and raw.stride(1) % 4 == 0
-        # 500 ms mode: the streaming kernel fetches rows of any alignment itself (TMA bulk copies, else 8- / 4-byte cp.async)
-        if aligned or mode == _lib.MODE_500MS or n_blocks == 0 or t_len < 40 * 2600:
-            _lib.check(lib.eegfe_de_psd_from_raw(
-                raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), mode,
-                de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
-        else:
-            # 1 s / 2 s modes: rows that are only 4-byte aligned (odd block length / strides) cannot be fetched by the
-            # ring kernel's TMA bulk copies.  Re-align them with the byte-exact clip gather (one extra HBM pass through a
-            # bounded scratch buffer) and run the fast kernels on that; libeegfe's own no-workspace fallback for such
-            # rows is 2-60x slower.
-            chunk = max(1, min(n_blocks, 28))
-            scratch = torch.empty((chunk * 200, n_ch, 400), dtype=torch.float32, device=raw.device)
-            for lo in range(0, n_blocks, chunk):
-                nb = min(chunk, n_blocks - lo)
-                part = raw[lo:lo + nb]
-                _lib.check(lib.eegfe_segment_clips(part.data_ptr(), _lib.DTYPE_F32, nb, n_ch, t_len, raw.stride(0),
-                                                   raw.stride(1), 200, scratch.data_ptr(), _stream(raw)))
-                _lib.check(lib.eegfe_de_psd_from_clips(scratch.data_ptr(), nb * 200, n_ch, mode,
-                                                       de[lo * 200:].data_ptr(), psd[lo * 200:].data_ptr(),
-                                                       status.data_ptr(), _stream(raw)))
+        # rows of any alignment: 16-byte aligned rows ride on TMA bulk copies, others (an odd block length or stride) on
+        # the kernels' 8- / 4-byte cp.async loader -- no re-alignment pass, no scratch buffer
+        _lib.check(lib.eegfe_de_psd_from_raw(
+            raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), mode,
+            de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
     return de, psd, status
 
 

@@ -227,7 +227,7 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 /* Number of kernels this library has launched since load (gpu_launches accounting in bench.py). */
 int64_t eegfe_launch_count(void);
 
-/* Tile loader of the 200-sample-row kernels (2 s mode, pre-cut 200 / 400-sample windows).  Default (0): one 1-D TMA
+/* Tile loader of the 200-sample-row kernels (2 s mode, pre-cut 400-sample windows).  Default (0): one 1-D TMA
  * bulk copy per row.  1: clip-aligned tiles fetched by ONE TMA tensor copy each (cp.async.bulk.tensor, tensor map built
  * per launch, L2 promotion off) -- slower on B200 (6.0 vs 6.85 G channel-windows/s in 2 s mode), kept for traffic
  * measurements.  Process-wide; returns the previous setting.  eegfe_tma_launch_count(): launches that used it. */
