@@ -290,6 +290,33 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
 #include "eegfe_stream.cuh"
 namespace eegfe {
 
+// Ring-kernel producer, rows that are only 8- / 4-byte aligned (an odd block length or stride): cp.async instead of TMA
+// bulk copies, one row per step, lanes side by side; the phase completes when this warp's copies have landed.
+template <class C>
+__device__ __noinline__ void ring_load_tile_small(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
+                                                  unsigned generation, unsigned row0, unsigned nrows)
+{
+  const Job& job = *jobp;
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) st_release_smem(armed, generation + 1u);
+#pragma unroll 1
+  for (unsigned r = 0; r < nrows; ++r) {
+    const float* src = job.in + row_offset(job, row0 + r, C::kWindows, nullptr);
+    float* dst = slot + r * C::kRowStride;
+    if (job.row_align == 8) {
+#pragma unroll 1
+      for (int i = 2 * lane; i < C::kLoad; i += 64) cp_async_small<8>(dst + i, src + i);
+    } else {
+#pragma unroll 1
+      for (int i = lane; i < C::kLoad; i += 32) cp_async_small<4>(dst + i, src + i);
+    }
+  }
+  cp_async_track(bar);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // the ring kernel (rows 16-byte aligned; 1 s / 2 s modes, pre-cut 1 s windows): warp-specialised, no block-wide
 // barrier in the steady state
@@ -394,26 +421,9 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
         __syncwarp();
         continue;
       }
-      if (job.row_align < 16) {
-        // rows that are only 8- / 4-byte aligned (odd block length or stride): cp.async instead of TMA bulk copies, one
-        // row per step, lanes side by side; the phase completes when this warp's copies have landed
-        if (lane == 0) st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
-#pragma unroll 1
-        for (unsigned r = 0; r < nrows; ++r) {
-          const float* src = job.in + row_offset(job, row0 + r, C::kWindows, nullptr);
-          float* dst = ring + s * C::kSlotFloats + r * C::kRowStride;
-          if (job.row_align == 8) {
-#pragma unroll 1
-            for (int i = 2 * lane; i < C::kLoad; i += 64) cp_async_small<8>(dst + i, src + i);
-          } else {
-#pragma unroll 1
-            for (int i = lane; i < C::kLoad; i += 32) cp_async_small<4>(dst + i, src + i);
-          }
-        }
-        cp_async_track(&full_bar[s]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-        __syncwarp();
+      if (job.row_align < 16) {            // cold path, out of line (cp.async instead of TMA bulk copies)
+        ring_load_tile_small<C>(&job, ring + s * C::kSlotFloats, &full_bar[s], &armed[s],
+                                static_cast<unsigned>(m / C::kSlots), row0, nrows);
         continue;
       }
       if (lane == 0) {
