@@ -200,7 +200,8 @@ def test_gpu_graphed_build_replays_with_new_features(gold):
     graphed = consumers.GraphedBuild(build, feat)
     want = consumers.semantic_predictor_inputs(feat, gt, chosen)[0]
     assert torch.equal(graphed.replay(), want)
-    feat.mul_(1.5).add_(0.25)                                    # new features, same buffer
+    feat.add_(torch.randn(feat.shape, device=feat.device, generator=torch.Generator(feat.device).manual_seed(3)) * 500)
+    # ^ new features in the same buffer (not an affine map of the old ones: standardising would undo that)
     want2 = consumers.semantic_predictor_inputs(feat, gt, chosen)[0]
     before = _lib.launch_count()
     got2 = graphed.replay()
