@@ -314,6 +314,8 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    if args.tensor_loads:
+        _lib.set_tensor_loads(True)
     mode = args.mode
     mode_id = frontend.MODES[mode]
     S = args.subjects
@@ -897,6 +899,8 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--skip-other-modes", action="store_true")
+    ap.add_argument("--tensor-loads", action="store_true",
+                    help="measurement option: 2 s tiles by one TMA tensor copy each (eegfe_set_tensor_loads)")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":

@@ -311,9 +311,7 @@ __device__ __noinline__ void ring_load_tile_small(const Job* jobp, float* slot, 
       for (int i = lane; i < C::kLoad; i += 32) cp_async_small<4>(dst + i, src + i);
     }
   }
-  cp_async_track(bar);
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
+  cp_async_arrive(bar);
   __syncwarp();
 }
 
@@ -384,7 +382,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < C::kSlots; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], full_barrier_arrivals(job));
       mbar_init(&empty_bar[s], C::kGroupWarps);
       armed[s] = 0;
     }

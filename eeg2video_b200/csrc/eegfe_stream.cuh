@@ -113,11 +113,15 @@ __device__ __forceinline__ void cp_async_small(void* dst_smem, const void* src_g
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
-// the executing thread's earlier cp.async count as one more pending arrival on `bar` until they have landed
-__device__ __forceinline__ void cp_async_track(uint64_t* bar)
+// one arrival on `bar`, delivered when the executing thread's earlier cp.async have landed (.noinc: it counts against
+// the barrier's init count -- 32 per phase in the cp.async mode, one per lane of the loading warp)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
 {
-  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrivals that complete a phase of a slot's `full` barrier: 1 (arrive.expect_tx by the lane that issues the TMA copies)
+// or, for rows TMA cannot fetch, the 32 lanes of the warp that issues the cp.async copies
+__device__ __forceinline__ unsigned full_barrier_arrivals(const Job& job) { return job.row_align < 16 ? 32u : 1u; }
 
 // Rows that are only 8- or 4-byte aligned (job.row_align; an odd block length or stride): 8- / 4-byte cp.async
 // (LDGSTS), one row per step, lanes side by side; the barrier phase completes when the issuing warp's copies have landed.
@@ -140,9 +144,7 @@ __device__ __noinline__ void stream_load_tile_small(const Job* jobp, float* slot
       for (int i = lane; i < SC::kLoad; i += 32) cp_async_small<4>(dst + i, src + i);
     }
   }
-  cp_async_track(bar);                     // every lane: +1 pending arrival until its copies are in shared memory
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar);         // the phase's own arrival, after all 32 have been registered
+  cp_async_arrive(bar);                    // every lane: its arrival fires when its copies are in shared memory
   __syncwarp();
 }
 
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < C::kSlots; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], full_barrier_arrivals(job));
       consumed[s] = 0;
       staged[s] = 0;
       drained[s] = 0;
