@@ -53,6 +53,16 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress notes on stderr (the JSON line is the only thing on stdout)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write(f"[bench {time.perf_counter() - _T0:7.1f} s] {msg}\n")
+        sys.stderr.flush()
+
+
 METRIC = "de_psd_channel_windows_per_s"
 UNIT = "channel-windows/s"
 
@@ -330,6 +340,7 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log("resident batch ready; parity gate")
     # ---- parity gate on EVERY rank's first subject (oracle = checker only); the line reports the worst rank ----
     parity = None
     if not args.skip_parity:
@@ -356,6 +367,7 @@ def run_gpu_arm(args):
         if not (parity["segmentation_bit_exact"] and parity["psd_max_rel"] <= 1e-4 and parity["de_max_abs"] <= 1e-4):
             raise SystemExit(f"parity gate failed: {parity}")
 
+    log("timed region")
     # ---- device-resident throughput: K launches of the fused kernel, CUDA events on the launch stream ----
     with torch.cuda.device(dev):
         de_buf = torch.empty((S * 7 * 200, ops.WINDOWS_PER_CLIP[mode_id], 62, 5), dtype=torch.float32, device=dev)
@@ -399,6 +411,7 @@ def run_gpu_arm(args):
     gpu_launches = _lib.launch_count() - launches_before
     value = world * cw_step_gpu * args.steps / (elapsed_ms * 1e-3)
 
+    log("sustained run")
     # ---- the same launches back to back for >= args.sustain_s seconds, on every rank: the throughput the 1 kW power
     #      cap allows (`value` above is a ~25 ms burst entered from idle), timed with CUDA events like `value`, with
     #      the SM clock sampled over exactly this window ----
@@ -428,6 +441,7 @@ def run_gpu_arm(args):
         if sustained is not None:
             sustained["clocks"] = per_window["sustained"]
 
+    log("single subject, other modes, next rows")
     # ---- BASELINE configs[1] as written: ONE subject, one launch (latency-bound; SURVEY.md 8d asks for us per call) ----
     single = None
     if rank == 0:
@@ -592,6 +606,7 @@ def run_gpu_arm(args):
         del graphed, g_out, c_ref
         del f_de, f_units, c_out
 
+    log("end to end")
     # ---- end to end: pinned host recordings -> H2D -> fused kernel -> D2H of the features, every step ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     numa_cpus = pipeline.bind_to_gpu_numa_node(dev) if world > 1 else None     # node-local pinned buffers per rank
@@ -642,6 +657,7 @@ def run_gpu_arm(args):
     e2e_ok = max_over_ranks(0.0 if e2e_ok_local else 1.0) == 0.0           # every rank's host result == its device result
     e2e_launches = _lib.launch_count() - launches_e2e0
 
+    log("gather")
     # ---- final gather of the feature tensors to rank 0 (the only exchange; reported, not in `value`) ----
     def check_every_rank(full_de, full_psd, per_rank, pick):
         """rank 0: recompute one subject of EVERY rank's shard locally (subjects are seeded by global id) and compare
@@ -751,6 +767,7 @@ def run_gpu_arm(args):
                 "all_ranks_match": bool(both_ok),
                 "note": "round-1 path (NCCL gather of both tensors after the kernels), kept as the comparison"}}
 
+    log("cohort")
     # ---- BASELINE configs[3] as written: the 1000-subject cohort, 500 ms sliding windows, sharded by subject ----
     cohort_big = None
     if args.cohort_subjects > 0:
@@ -809,6 +826,7 @@ def run_gpu_arm(args):
                      "kernels are timed (one CUDA event pair per launch); there is no gather at 1 GPU")}
         del big_de, big_psd, out_big
 
+    log("cpu baseline, report")
     if rank == 0:
         peak, peak_src = measured_peaks()
         kernel_ms = elapsed_ms / args.steps                       # one launch per step
