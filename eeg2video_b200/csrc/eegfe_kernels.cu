@@ -835,6 +835,12 @@ static int launch_stream(const Job& job, cudaStream_t stream)
     } else {
       return EEGFE_EINVAL;
     }
+  } else if (job.row_align < 16) {
+    // rows TMA cannot fetch: the cp.async instantiation (a kernel of its own; the TMA kernel carries none of its code)
+    static std::atomic<unsigned long long> configured_small{0};
+    const int rc = configure_smem(configured_small, de_psd_stream_kernel<SC, false, true>, SC::kSmemBytes);
+    if (rc != 0) return rc;
+    de_psd_stream_kernel<SC, false, true><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
   } else {
     const int rc = configure_smem(configured, de_psd_stream_kernel<SC, false>, SC::kSmemBytes);
     if (rc != 0) return rc;
@@ -844,7 +850,7 @@ static int launch_stream(const Job& job, cudaStream_t stream)
   return static_cast<int>(cudaGetLastError());
 }
 
-// ---- window-box kernel (eegfe_tma.cuh): tensor map over the recording, one TMA tensor copy per tile ----
+// ---- tensor maps for the ring kernel's optional tensor-copy producer ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -123,11 +123,13 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
 // or, for rows TMA cannot fetch, the 32 lanes of the warp that issues the cp.async copies
 __device__ __forceinline__ unsigned full_barrier_arrivals(const Job& job) { return job.row_align < 16 ? 32u : 1u; }
 
-// Rows that are only 8- or 4-byte aligned (job.row_align; an odd block length or stride): 8- / 4-byte cp.async
-// (LDGSTS), one row per step, lanes side by side; the barrier phase completes when the issuing warp's copies have landed.
+// Rows that are only 8- or 4-byte aligned (job.row_align; an odd block length or stride) cannot ride on TMA bulk copies:
+// the SMALL instantiation of the kernel fetches them with 8- / 4-byte cp.async (LDGSTS), one row per step, lanes side
+// by side; every lane's arrival on the slot's barrier (32 per phase in this instantiation) fires when its copies have
+// landed.  It is a separate kernel so that the TMA kernel's hot loop carries none of this code.
 template <class SC>
-__device__ __noinline__ void stream_load_tile_small(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
-                                                    unsigned generation, unsigned row0, int nrows)
+__device__ __forceinline__ void stream_load_tile_small(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
+                                                       unsigned generation, unsigned row0, int nrows)
 {
   const Job& job = *jobp;
   const int lane = threadIdx.x & 31;
@@ -150,16 +152,16 @@ __device__ __noinline__ void stream_load_tile_small(const Job* jobp, float* slot
 
 // whole warp: re-arm `bar` and issue the bulk copies of the tile starting at global row `row0`: one per row, or a
 // single one when the rows sit back to back in HBM exactly as they do in the slot (pre-cut windows, dense array).
-template <class SC>
+template <class SC, bool SMALL>
 __device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
                                                    unsigned generation, unsigned row0, int nrows)
 {
-  const Job& job = *jobp;
-  const int lane = threadIdx.x & 31;
-  if (job.row_align < 16) {                  // cold path, kept out of line: the hot loop stays inside the instruction cache
+  if constexpr (SMALL) {
     stream_load_tile_small<SC>(jobp, slot, bar, armed, generation, row0, nrows);
     return;
   }
+  const Job& job = *jobp;
+  const int lane = threadIdx.x & 31;
   fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy refill
   if (lane == 0) {
     mbar_arrive_expect_tx(bar, nrows * SC::kRowBytes);
@@ -220,7 +222,7 @@ __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const flo
   }
 }
 
-template <class SC, bool NORM>
+template <class SC, bool NORM, bool SMALL = false>
 __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __grid_constant__ Job job)
 {
   using C = SC;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < C::kSlots; ++s) {
-      mbar_init(&full_bar[s], full_barrier_arrivals(job));
+      mbar_init(&full_bar[s], SMALL ? 32 : 1);
       consumed[s] = 0;
       staged[s] = 0;
       drained[s] = 0;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
     const unsigned w = tid >> 5;
     if (w < C::kSlots && w < n_mine) {
       const unsigned row0 = tile_row0(w);
-      stream_load_tile<C>(&job, ring + w * C::kSlotFloats, &full_bar[w], &armed[w], 0u, row0, tile_nrows(row0));
+      stream_load_tile<C, SMALL>(&job, ring + w * C::kSlotFloats, &full_bar[w], &armed[w], 0u, row0, tile_nrows(row0));
     }
   }
 
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
       if (last & 1u) {
         if (tk + C::kSlots < n_mine) {
           const unsigned r0 = tile_row0(tk + C::kSlots);
-          stream_load_tile<C>(&job, ring + sk * C::kSlotFloats, &full_bar[sk], &armed[sk], tk / C::kSlots + 1, r0,
+          stream_load_tile<C, SMALL>(&job, ring + sk * C::kSlotFloats, &full_bar[sk], &armed[sk], tk / C::kSlots + 1, r0,
                               tile_nrows(r0));
         }
       }
