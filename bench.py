@@ -630,6 +630,8 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * cw_step_gpu * e2e_steps / e2e_s
+    e2e_ok_local = bool(torch.equal(de_host, de_buf.cpu()) and torch.equal(psd_host, psd_buf.cpu()))
+    e2e_ok = max_over_ranks(0.0 if e2e_ok_local else 1.0) == 0.0           # every rank's host result == its device result
 
     # ---- what the host can deliver: every rank copies its pinned recordings to its GPU at the same time, plain
     #      contiguous cudaMemcpyAsync (the ceiling of any upload scheme), then the same pipeline with contiguous
@@ -640,7 +642,20 @@ def run_gpu_arm(args):
         raw.copy_(raw_host, non_blocking=True)
     torch.cuda.synchronize()
     h2d_ceiling = 2 * raw_host.numel() * 4 / max_over_ranks(time.perf_counter() - t0) / 1e9      # GB/s per GPU
+    # ... and with the features flowing back at the same time, as they do in the pipeline (0.175 B down per B up)
+    side = torch.cuda.Stream()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        raw.copy_(raw_host, non_blocking=True)
+        with torch.cuda.stream(side):
+            de_host.copy_(de_buf, non_blocking=True)
+            psd_host.copy_(psd_buf, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_ceiling_duplex = 2 * raw_host.numel() * 4 / max_over_ranks(time.perf_counter() - t0) / 1e9
     pipe_c = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode, compact=False)
+    de_host.zero_()
+    psd_host.zero_()
     pipe_c.run(raw_host, de_host, psd_host)
     barrier()
     t0 = time.perf_counter()
@@ -653,8 +668,6 @@ def run_gpu_arm(args):
                   "h2d_gbs_per_gpu": pipe_c.h2d_bytes(S * 7) / (e2e_c_s / e2e_steps) / 1e9,
                   "matches_device_result": max_over_ranks(0.0 if torch.equal(de_host, de_buf.cpu()) else 1.0) == 0.0}
     del pipe_c
-    e2e_ok_local = bool(torch.equal(de_host, de_buf.cpu()) and torch.equal(psd_host, psd_buf.cpu()))
-    e2e_ok = max_over_ranks(0.0 if e2e_ok_local else 1.0) == 0.0           # every rank's host result == its device result
     e2e_launches = _lib.launch_count() - launches_e2e0
 
     log("gather")
@@ -676,10 +689,15 @@ def run_gpu_arm(args):
         buffers (chunk after chunk, in call order), one CUDA event pair around each launch -- so that what the events
         measure is kernels, not the caching allocator."""
 
-        def __init__(self, n_local):
+        def __init__(self, n_local, into=None):
+            """into: (de, psd) tensors whose first n_local subjects receive the features (rank 0 passes its own slice
+            of the cohort tensors, so that nothing has to be copied there afterwards)."""
             shape = (n_local, 7 * 200, ops.WINDOWS_PER_CLIP[mode_id], 62, 5)
-            self.de = torch.empty(shape, dtype=torch.float32, device=dev)
-            self.psd = torch.empty_like(self.de)
+            if into is None:
+                self.de = torch.empty(shape, dtype=torch.float32, device=dev)
+                self.psd = torch.empty_like(self.de)
+            else:
+                self.de, self.psd = (t[:n_local].reshape(shape) for t in into)
             self.events, self.at = [], 0
 
         def reset(self):
@@ -731,7 +749,7 @@ def run_gpu_arm(args):
         # (b) the product path, compute INCLUDED: cohort.process_cohort -- chunked kernels, PSD only over point-to-point
         #     NCCL as each chunk finishes, DE rebuilt on rank 0 (eegfe_de_from_psd)
         chunk = max(1, S // args.gather_chunks)
-        kern = ShardKernels(S)
+        kern = ShardKernels(S, into=out_full)
         for i in range(1 + reps):
             if i == 1:
                 barrier()
@@ -778,12 +796,12 @@ def run_gpu_arm(args):
         free_b = torch.cuda.mem_get_info(dev)[0]
         resident = n_local * synth.BYTES_PER_SUBJECT + (n_local + (total if rank == 0 else 0)) * 24.304e6 < 0.8 * free_b
         chunk_c = args.cohort_chunk
-        kern = ShardKernels(n_local)
         big_shape = (total, 7, 40, 5) + ((ops.WINDOWS_PER_CLIP[mode_id],) if ops.WINDOWS_PER_CLIP[mode_id] > 1 else ()) + (62, 5)
         out_big = None
         if rank == 0:
             out_big = (torch.empty(big_shape, dtype=torch.float32, device=dev),
                        torch.empty(big_shape, dtype=torch.float32, device=dev))
+        kern = ShardKernels(n_local, into=out_big)
         if resident:
             big = synth.synth_cohort(range(lo_g, hi_g), dev)
             loader = lambda lo, hi: big[lo:hi]                               # noqa: E731
@@ -874,6 +892,8 @@ def run_gpu_arm(args):
                     "h2d_gbs_per_gpu": pipe.h2d_bytes(S * 7) / (e2e_s / e2e_steps) / 1e9,
                     "h2d_ceiling_gbs_per_gpu": h2d_ceiling, "h2d_ceiling_gbs_aggregate": h2d_ceiling * world,
                     "h2d_frac_of_ceiling": pipe.h2d_bytes(S * 7) / (e2e_s / e2e_steps) / 1e9 / h2d_ceiling,
+                    "h2d_ceiling_with_d2h_gbs_per_gpu": h2d_ceiling_duplex,
+                    "h2d_frac_of_ceiling_with_d2h": pipe.h2d_bytes(S * 7) / (e2e_s / e2e_steps) / 1e9 / h2d_ceiling_duplex,
                     "h2d_ceiling_how": "all ranks at once: 2 x contiguous pinned cudaMemcpyAsync of the resident batch, "
                                        "max over ranks",
                     "contiguous_upload": e2e_contig,

@@ -183,8 +183,10 @@ def run_cohort(n_local, loader, n_subjects_total, mode="500ms", chunk_subjects=N
             if psd is None:
                 de, psd = fn(loader(*own))
             lo, hi = starts[rank] + own[0], starts[rank] + own[1]
-            full_psd[lo:hi].copy_(psd)
-            full_de[lo:hi].copy_(de)
+            if psd.data_ptr() != full_psd[lo:hi].data_ptr():       # a compute hook may write straight into `out`
+                full_psd[lo:hi].copy_(psd)
+            if de.data_ptr() != full_de[lo:hi].data_ptr():
+                full_de[lo:hi].copy_(de)
         if pending:
             finish(pending.pop(0))                             # DE of round k - 1 while round k is in flight
         pending.append((reqs, spans))
