@@ -17,20 +17,20 @@ __global__ void __launch_bounds__(256) select_units_kernel(const float* __restri
                                                             long long n_out, int n_windows, int cols, int reduce,
                                                             float* __restrict__ out)
 {
-  const long long per_unit = reduce ? cols : static_cast<long long>(n_windows) * cols;
-  const long long total = n_out * per_unit;
+  // one output unit per block step, threads along the unit's columns: no per-element division, coalesced both ways
+  const int per_unit = reduce ? cols : n_windows * cols;
   const float inv_w = 1.0f / static_cast<float>(n_windows);
-  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
-       e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long j = e / per_unit;
-    const long long i = e - j * per_unit;
-    const float* p = feat + static_cast<long long>(src[j]) * n_windows * cols + i;
-    if (reduce) {
-      float acc = p[0];
-      for (int w = 1; w < n_windows; ++w) acc = __fadd_rn(acc, p[static_cast<long long>(w) * cols]);
-      out[e] = n_windows == 1 ? acc : (n_windows == 2 ? acc * 0.5f : acc * inv_w);
-    } else {
-      out[e] = p[0];
+  for (long long j = blockIdx.x; j < n_out; j += gridDim.x) {
+    const float* unit = feat + static_cast<long long>(src[j]) * n_windows * cols;
+    float* o = out + j * per_unit;
+    for (int i = threadIdx.x; i < per_unit; i += blockDim.x) {
+      if (reduce) {
+        float acc = unit[i];
+        for (int w = 1; w < n_windows; ++w) acc = __fadd_rn(acc, unit[static_cast<long long>(w) * cols + i]);
+        o[i] = n_windows == 1 ? acc : (n_windows == 2 ? acc * 0.5f : acc * inv_w);
+      } else {
+        o[i] = unit[i];
+      }
     }
   }
 }
@@ -55,13 +55,22 @@ __global__ void __launch_bounds__(256) column_partial_kernel(const float* __rest
   for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
     const double m = PASS == 1 ? shift[c] : 0.0;
     double acc = 0.0, lin = 0.0;
-    for (long long r = r0; r < r1; ++r) {
-      const double d = static_cast<double>(x[r * row_stride + c]) - m;
-      if (PASS == 1) {
-        acc += d * d;
-        lin += d;
-      } else {
-        acc += d;
+    // eight loads in flight per thread, summed in row order (the order is part of the result: deterministic)
+    for (long long rb = r0; rb < r1; rb += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = rb + k < r1 ? x[(rb + k) * row_stride + c] : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (rb + k < r1) {
+          const double d = static_cast<double>(v[k]) - m;
+          if (PASS == 1) {
+            acc += d * d;
+            lin += d;
+          } else {
+            acc += d;
+          }
+        }
       }
     }
     partial[static_cast<long long>(blockIdx.x) * n_cols + c] = acc;
@@ -114,12 +123,12 @@ __global__ void __launch_bounds__(256) standardize_kernel(const float* __restric
   mean += static_cast<long long>(blockIdx.y) * n_cols;
   scale += static_cast<long long>(blockIdx.y) * n_cols;
   out += static_cast<long long>(blockIdx.y) * n_rows * n_cols;
-  const long long total = n_rows * n_cols;
-  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
-       e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = e / n_cols;
-    const int c = static_cast<int>(e - r * n_cols);
-    out[e] = static_cast<float>((static_cast<double>(x[r * row_stride + c]) - mean[c]) / scale[c]);
+  // one row per block step, threads along the columns (no 64-bit division per element)
+  for (long long r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const float* xr = x + r * row_stride;
+    float* o = out + r * n_cols;
+    for (int c = threadIdx.x; c < n_cols; c += blockDim.x)
+      o[c] = static_cast<float>((static_cast<double>(xr[c]) - mean[c]) / scale[c]);
   }
 }
 

@@ -1345,8 +1345,7 @@ int eegfe_select_units(const float* feat, int64_t n_units_in, int n_windows, int
   if (n_units_in < 0 || n_out < 0 || n_windows <= 0 || n_cols <= 0) return EEGFE_EINVAL;
   if (n_out == 0) return 0;
   if (feat == nullptr || src_index == nullptr || out == nullptr) return EEGFE_EINVAL;
-  const long long total = n_out * (reduce_windows ? n_cols : static_cast<long long>(n_windows) * n_cols);
-  long long blocks = (total + 255) / 256;
+  long long blocks = n_out;
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   select_units_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -1396,8 +1395,7 @@ int eegfe_standardize(const float* x, int64_t n_groups, int64_t n_rows, int n_co
   if (n_groups < 0 || n_rows < 0 || n_cols <= 0 || row_stride < n_cols || group_stride < 0) return EEGFE_EINVAL;
   if (n_rows == 0 || n_groups == 0) return 0;
   if (x == nullptr || mean == nullptr || scale == nullptr || out == nullptr || n_groups > 65535) return EEGFE_EINVAL;
-  const long long total = n_rows * n_cols;
-  long long blocks = (total + 255) / 256;
+  long long blocks = n_rows;
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   const dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(n_groups));
