@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--launches", type=int, default=20)
     ap.add_argument("--peak", type=float, default=6541.8)
+    ap.add_argument("--block-len", type=int, default=104000,
+                    help="samples per channel row; 104001 / 104002 make the rows 4- / 8-byte aligned only (cp.async loader)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128), 0 = leave")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -47,7 +49,7 @@ def main():
         val2 = ctypes.c_size_t()
         rt.cudaDeviceGetLimit(ctypes.byref(val2), 5)
         print(f"cudaLimitMaxL2FetchGranularity {val.value} -> {val2.value} (rc {rc})")
-    n_blocks, n_ch, t_len = args.subjects * 7, 62, 104000
+    n_blocks, n_ch, t_len = args.subjects * 7, 62, args.block_len
     g = torch.Generator(device=dev).manual_seed(1)
     raw = torch.randn((n_blocks, n_ch, t_len), device=dev, generator=g) * 30.0
     fns = [(p, load(p)) for p in args.libs]
