@@ -42,6 +42,7 @@ SIGNATURES = {
     "eegfe_launch_count": (_i64, []),
     "eegfe_tma_launch_count": (_i64, []),
     "eegfe_set_tensor_loads": (_int, [_int]),
+    "eegfe_set_cta_limit": (_int, [_int]),
 }
 
 _lib = None
@@ -88,6 +89,11 @@ def launch_count():
 
 def tma_launch_count():
     return int(load().eegfe_tma_launch_count())
+
+
+def set_cta_limit(max_ctas):
+    """Cap the persistent kernels' grid (0 = one CTA per SM); returns the previous cap."""
+    return int(load().eegfe_set_cta_limit(int(max_ctas)))
 
 
 def set_tensor_loads(on):

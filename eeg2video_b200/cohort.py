@@ -19,10 +19,33 @@ Works with any torch.distributed backend: NCCL on the GPUs, gloo in the CPU test
 gather logic with stand-in compute functions; the kernels are covered by the gpu tests, the NCCL path by
 tests/test_cohort_nccl.py).
 """
+import contextlib
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import frontend
+
+# SMs a rank leaves to NCCL while a gather is in flight (the feature kernels otherwise fill every SM and the NCCL send /
+# receive kernels wait for a CTA to retire): the gathering rank receives from world - 1 peers, a sender feeds one.
+RESERVED_SMS_DST = int(os.environ.get("EEGFE_COHORT_RESERVED_SMS_DST", "20"))
+RESERVED_SMS_SRC = int(os.environ.get("EEGFE_COHORT_RESERVED_SMS_SRC", "8"))
+
+
+@contextlib.contextmanager
+def _leave_sms_to_nccl(device, reserved):
+    """Cap the persistent kernels' grid at (SMs - reserved) for the duration of a distributed cohort run."""
+    if reserved <= 0 or device is None or device.type != "cuda":
+        yield
+        return
+    from . import _lib
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    old = _lib.set_cta_limit(max(1, sms - reserved))
+    try:
+        yield
+    finally:
+        _lib.set_cta_limit(old)
 
 
 def shard_bounds(n_items, rank, world):
@@ -115,7 +138,20 @@ def process_shard(raw, mode="500ms", chunk_subjects=None, compute=None):
 
 
 def run_cohort(n_local, loader, n_subjects_total, mode="500ms", chunk_subjects=None, group=None, compute=None,
-               rebuild_de=None, dst=0, out=None):
+               rebuild_de=None, dst=0, out=None, device=None):
+    """Shard-local compute, chunk by chunk, + PSD-only point-to-point gather + DE rebuilt on rank `dst`.
+    See _run_cohort for the arguments; `device` (default: the current CUDA device when the backend is NCCL) is the GPU
+    whose feature kernels leave RESERVED_SMS_* SMs to the NCCL kernels while the gather is in flight."""
+    if _distributed(group) and dist.get_backend(group) == "nccl":
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        reserved = RESERVED_SMS_DST if dist.get_rank(group) == dst else RESERVED_SMS_SRC
+        with _leave_sms_to_nccl(dev, reserved):
+            return _run_cohort(n_local, loader, n_subjects_total, mode, chunk_subjects, group, compute, rebuild_de, dst, out)
+    return _run_cohort(n_local, loader, n_subjects_total, mode, chunk_subjects, group, compute, rebuild_de, dst, out)
+
+
+def _run_cohort(n_local, loader, n_subjects_total, mode="500ms", chunk_subjects=None, group=None, compute=None,
+                rebuild_de=None, dst=0, out=None):
     """Shard-local compute, chunk by chunk, + PSD-only point-to-point gather + DE rebuilt on rank `dst`.
 
     loader(lo, hi) -> raw recordings (hi - lo, 7, ch, T) of this rank's LOCAL subjects lo..hi-1 on this rank's device

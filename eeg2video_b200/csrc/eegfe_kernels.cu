@@ -792,6 +792,17 @@ static int device_ordinal()
   return dev % kMaxDevices;
 }
 
+// Optional cap on the CTAs of the persistent feature kernels (0 = one per SM).  The kernels occupy an SM completely (all
+// registers, ~207 KB of shared memory), so a concurrent NCCL send / receive kernel cannot start until some CTA retires:
+// during a cohort gather the ranks leave a few SMs free (cohort.run_cohort) and the transfers overlap the FFTs.
+static std::atomic<int> g_cta_limit{0};
+
+static unsigned persistent_grid(unsigned wanted)
+{
+  const int cap = g_cta_limit.load(std::memory_order_relaxed);
+  return (cap > 0 && wanted > static_cast<unsigned>(cap)) ? static_cast<unsigned>(cap) : wanted;
+}
+
 static int sm_count()
 {
   static std::atomic<int> n[kMaxDevices];
@@ -823,7 +834,7 @@ static int launch_stream(const Job& job, cudaStream_t stream)
 {
   if (job.total_rows == 0) return 0;
   const unsigned n_tiles = (job.total_rows + SC::kRows - 1) / SC::kRows;
-  unsigned grid = static_cast<unsigned>(sm_count());
+  unsigned grid = persistent_grid(static_cast<unsigned>(sm_count()));
   if (grid > n_tiles) grid = n_tiles;
   constexpr bool kCanNorm = SC::kLoad == 400 && SC::kWindows == 7;
   static std::atomic<unsigned long long> configured{0}, configured_norm{0};
@@ -958,7 +969,7 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
           if (job.tiles_per_clip) n_tiles = (job.total_rows / job.n_ch) * job.tiles_per_clip;
         }
       }
-      unsigned grid = static_cast<unsigned>(sm_count()) * C::kCtasPerSm;
+      unsigned grid = persistent_grid(static_cast<unsigned>(sm_count()) * C::kCtasPerSm);
       if (grid > n_tiles) grid = n_tiles;
       static std::atomic<unsigned long long> configured{0};
       const int rc = configure_smem(configured, de_psd_kernel<C>, C::kSmemBytes);
@@ -1424,6 +1435,11 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 int64_t eegfe_launch_count(void) { return g_launches.load(); }
 
 int64_t eegfe_tma_launch_count(void) { return g_tma_launches.load(); }
+
+int eegfe_set_cta_limit(int max_ctas)
+{
+  return g_cta_limit.exchange(max_ctas > 0 ? max_ctas : 0);
+}
 
 int eegfe_set_tensor_loads(int on)
 {

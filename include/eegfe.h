@@ -227,6 +227,12 @@ int eegfe_launch_geometry(int mode, int* grid, int* block, int* smem_bytes, int*
 /* Number of kernels this library has launched since load (gpu_launches accounting in bench.py). */
 int64_t eegfe_launch_count(void);
 
+/* Cap the grid of the persistent feature kernels at `max_ctas` CTAs (0 = one per SM, the default); returns the previous
+ * cap.  A CTA of these kernels fills its SM (registers, shared memory), so kernels of other streams -- NCCL's send /
+ * receive kernels during the cohort gather -- only start when a CTA retires; leaving a few SMs free lets them overlap.
+ * Process-wide. */
+int eegfe_set_cta_limit(int max_ctas);
+
 /* Tile loader of the 200-sample-row kernels (2 s mode, pre-cut 400-sample windows).  Default (0): one 1-D TMA
  * bulk copy per row.  1: clip-aligned tiles fetched by ONE TMA tensor copy each (cp.async.bulk.tensor, tensor map built
  * per launch, L2 promotion off) -- slower on B200 (6.0 vs 6.85 G channel-windows/s in 2 s mode), kept for traffic

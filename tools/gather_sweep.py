@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--subjects", type=int, default=24)
     ap.add_argument("--chunks", default="1,2,3,4,6,8")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--reserved", default="20:8", help="comma list of dst:src SMs left to NCCL (cohort.RESERVED_SMS_*)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -50,28 +51,30 @@ def main():
         at[0] += n
         return de.reshape(n, 7, 40, 5, 7, 62, 5), psd.reshape(n, 7, 40, 5, 7, 62, 5)
 
-    for n_chunks in [int(c) for c in args.chunks.split(",")]:
-        chunk = max(1, -(-S // n_chunks))
-        times = []
-        for i in range(1 + args.reps):
-            dist.barrier()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            at[0] = 0
-            a.record()
-            cohort.process_cohort(raw, S * world, chunk_subjects=chunk, compute=kern, out=out)
-            b.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            if i:
-                times.append(float(t.item()))
-        if rank == 0:
-            cw = world * S * 607600
-            best, med = min(times), sorted(times)[len(times) // 2]
-            print(f"chunks/rank {n_chunks:2d} (chunk {chunk:2d} subjects): best {best:6.3f} ms  median {med:6.3f} ms  "
-                  f"-> {cw / med / 1e6:6.2f} G cw/s with gather   NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}",
-                  flush=True)
+    for reserved in args.reserved.split(","):
+      cohort.RESERVED_SMS_DST, cohort.RESERVED_SMS_SRC = (int(v) for v in reserved.split(":"))
+      for n_chunks in [int(c) for c in args.chunks.split(",")]:
+          chunk = max(1, -(-S // n_chunks))
+          times = []
+          for i in range(1 + args.reps):
+              dist.barrier()
+              torch.cuda.synchronize()
+              a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+              at[0] = 0
+              a.record()
+              cohort.process_cohort(raw, S * world, chunk_subjects=chunk, compute=kern, out=out)
+              b.record()
+              torch.cuda.synchronize()
+              t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+              dist.all_reduce(t, op=dist.ReduceOp.MAX)
+              if i:
+                  times.append(float(t.item()))
+          if rank == 0:
+              cw = world * S * 607600
+              best, med = min(times), sorted(times)[len(times) // 2]
+              print(f"chunks/rank {n_chunks:2d} (chunk {chunk:2d} subjects): best {best:6.3f} ms  median {med:6.3f} ms  "
+                    f"-> {cw / med / 1e6:6.2f} G cw/s with gather   SMs left to NCCL dst:src = {reserved}",
+                    flush=True)
     dist.destroy_process_group()
 
 
