@@ -931,7 +931,7 @@ def main():
     ap.add_argument("--cpu-clips-per-step", type=int, default=40, help="clips per worker per CPU step")
     ap.add_argument("--sustain-s", "--clock-probe-s", dest="sustain_s", type=float, default=2.0,
                     help="seconds of back-to-back launches after the timed steps (sustained throughput + clocks); 0 = off")
-    ap.add_argument("--gather-chunks", type=int, default=4, help="kernel chunks per rank in the gather measurement")
+    ap.add_argument("--gather-chunks", type=int, default=8, help="kernel chunks per rank in the gather measurement")
     ap.add_argument("--cohort-subjects", type=int, default=1000, help="BASELINE configs[3] cohort size; 0 = skip")
     ap.add_argument("--cohort-chunk", type=int, default=25, help="subjects per kernel launch in the cohort run")
     ap.add_argument("--skip-cpu-baseline", action="store_true")

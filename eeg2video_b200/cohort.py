@@ -29,8 +29,10 @@ from . import frontend
 
 # SMs a rank leaves to NCCL while a gather is in flight (the feature kernels otherwise fill every SM and the NCCL send /
 # receive kernels wait for a CTA to retire): the gathering rank receives from world - 1 peers, a sender feeds one.
-RESERVED_SMS_DST = int(os.environ.get("EEGFE_COHORT_RESERVED_SMS_DST", "20"))
-RESERVED_SMS_SRC = int(os.environ.get("EEGFE_COHORT_RESERVED_SMS_SRC", "8"))
+# Measured on 8 B200s (tools/gather_sweep.py, 24 subjects per GPU, 8 chunks): compute + gather 4.09 ms with 0 / 0 SMs
+# left, 3.88 ms with 20 / 8, 3.51 ms with 32 / 8, 3.45 ms with 32 / 16, 3.54 ms with 48 / 8, 3.65 ms with 64 / 8.
+RESERVED_SMS_DST = int(os.environ.get("EEGFE_COHORT_RESERVED_SMS_DST", "32"))
+RESERVED_SMS_SRC = int(os.environ.get("EEGFE_COHORT_RESERVED_SMS_SRC", "16"))
 
 
 @contextlib.contextmanager

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--subjects", type=int, default=24)
     ap.add_argument("--chunks", default="1,2,3,4,6,8")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--reserved", default="20:8", help="comma list of dst:src SMs left to NCCL (cohort.RESERVED_SMS_*)")
+    ap.add_argument("--reserved", default="32:16", help="comma list of dst:src SMs left to NCCL (cohort.RESERVED_SMS_*)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
