@@ -13,7 +13,7 @@
 //                                             16 identical warps draw passes from a counter, tile duties fall to the
 //                                             last finisher
 //   this file          de_psd_kernel          1 s / 2 s windows: HBM-bound; producer warps + worker groups on a ring
-//                      de_psd_kernel_unaligned  rows that are only 4-byte aligned (no TMA): cooperative loads
+//                      (both)                 rows that are only 8- / 4-byte aligned: cp.async loader instead of TMA
 //                      gather / sliding-window / statistics kernels for the materialising and "next row" entry points
 //
 // C ABI: include/eegfe.h.  Reference semantics: see the citations in that header and in bandpower.cuh.
@@ -111,8 +111,7 @@ struct Cfg {
 // small tiles and as many surplus slots as shared memory holds; a tile is due every ~1 us per SM, so each group writes
 // its own tile and the producers only issue copies.  One bulk copy per row costs a producer warp ~30 issue cycles
 // (the TMA operands are per-lane, the instruction is uniform): two producer warps.
-// CfgSliding500 / CfgWin100 only parameterise the unaligned-row fallback kernel: with 16-byte aligned rows those two
-// shapes run on the streaming kernel (eegfe_stream.cuh).
+// CfgSliding500 / CfgWin100 only name the two shapes that run on the streaming kernel (eegfe_stream.cuh).
 //                         LOAD NWIN HOP NI  HANN          ROWS GRP SLOT CTAS PAD VEC SPLIT LANEMAP PROD
 using CfgSliding500 = Cfg<400, 7, 50, 4, kHannHalfSec, 32, 1, 2, 2, 4, 2, 1, true, 1>;
 using CfgOneSec     = Cfg<400, 2, 200, 8, kHannOneSec, 16, 7, 8, 1, 4, 4, 2, false, 2>;  // 7 x 64 + 64 thr, 218 KB
@@ -488,58 +487,6 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       if (store_tile<C, C::kGroupThreads>(job, out_a, out_b, row0, nrows, gt) && job.status != nullptr)
         atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// same arithmetic for rows that are only 4-byte aligned (odd block lengths / strides): TMA bulk copies need
-// 16-byte alignment, so this variant loads cooperatively, one stage, block barriers.  Correct, not tuned.
-// ---------------------------------------------------------------------------------------------------------------
-// A CTA works on kUnalignedTiles<C> tiles at a time (one sub-group of kUnits threads per tile) so that it has
-// >= 256 threads whatever the tile shape.
-template <class C>
-constexpr int kUnalignedTiles = (256 + C::kUnits - 1) / C::kUnits;
-
-template <class C>
-__global__ void __launch_bounds__(C::kUnits * kUnalignedTiles<C>, 1) de_psd_kernel_unaligned(const Job job)
-{
-  constexpr int M = kUnalignedTiles<C>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int sub = tid / C::kUnits;                       // which of the CTA's M tiles this thread works on
-  const int ut = tid - sub * C::kUnits;
-  float* const buf = reinterpret_cast<float*>(smem_raw) + sub * C::kSlotFloats;
-  const unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
-  int row_in_tile, w;
-  unit_to_row_window<C>(ut, row_in_tile, w);
-  for (unsigned tile0 = blockIdx.x * M; tile0 < n_tiles; tile0 += gridDim.x * M) {
-    const unsigned tile = tile0 + sub;
-    const unsigned row0 = tile * C::kRows;
-    unsigned nrows = 0;
-    if (tile < n_tiles) {
-      const unsigned left = job.total_rows - row0;
-      nrows = left < C::kRows ? left : C::kRows;
-    }
-    for (unsigned r = ut / 32; r < nrows; r += C::kUnits / 32) {
-      const float* src = job.in + row_offset(job, row0 + r, C::kWindows, nullptr);
-      for (int i = lane; i < C::kLoad; i += 32) buf[r * C::kRowStride + i] = __ldg(src + i);
-    }
-    __syncthreads();
-    if (static_cast<unsigned>(row_in_tile) < nrows) {
-      float e[5], psd[5], de[5];
-      window_band_energy<C::kNi, C::kHann, C::kVec>(buf + row_in_tile * C::kRowStride + w * C::kHop, e);
-      if (band_features(e, psd, de) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
-      int ob;
-      row_offset(job, row0 + row_in_tile, C::kWindows, &ob);
-      const int o = ob + w * static_cast<int>(job.n_ch) * 5;
-#pragma unroll
-      for (int b = 0; b < 5; ++b) {
-        job.de[o + b] = de[b];
-        job.psd[o + b] = psd[b];
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -977,15 +924,7 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
       de_psd_kernel<C><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
     }
   } else {
-    if (job.norm_out != nullptr) return EEGFE_EINVAL;     // the normalised-clip product needs 16-byte aligned rows
-    static std::atomic<unsigned long long> configured{0};
-    const int smem = C::kSlotFloats * 4 * kUnalignedTiles<C>;
-    const int rc = configure_smem(configured, de_psd_kernel_unaligned<C>, smem);
-    if (rc != 0) return rc;
-    unsigned grid = static_cast<unsigned>(sm_count()) * (smem <= 110 * 1024 ? 2 : 1);
-    const unsigned n_groups = (n_tiles + kUnalignedTiles<C> - 1) / kUnalignedTiles<C>;
-    if (grid > n_groups) grid = n_groups;
-    de_psd_kernel_unaligned<C><<<grid, C::kUnits * kUnalignedTiles<C>, smem, stream>>>(job);
+    return EEGFE_EINVAL;                     // the normalised-clip product needs 16-byte aligned rows
   }
   ++g_launches;
   return static_cast<int>(cudaGetLastError());
