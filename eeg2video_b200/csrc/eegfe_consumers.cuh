@@ -13,7 +13,7 @@ namespace eegfe {
 // out[j][i] for output unit j (a clip) and column i < cols = n_ch * 5:
 //   keep windows : out[(j * W + w) * cols + i] = feat[(src[j] * W + w) * cols + i]
 //   mean windows : out[j * cols + i] = (sum_w feat[(src[j] * W + w) * cols + i]) / W     (summed in window order)
-__global__ void __launch_bounds__(256) select_units_kernel(const float* __restrict__ feat, const int* __restrict__ src,
+__global__ void __launch_bounds__(512) select_units_kernel(const float* __restrict__ feat, const int* __restrict__ src,
                                                             long long n_out, int n_windows, int cols, int reduce,
                                                             float* __restrict__ out)
 {
@@ -41,7 +41,7 @@ constexpr int kStatRowsPerBlock = 64;
 // PASS 1: partial[b][c] = sum of (x - mean)^2 and partial[n_chunks + b][c] = sum of (x - mean) (the correction term of
 //         the corrected two-pass algorithm, sklearn/utils/extmath.py _incremental_mean_and_var).  float64, rows in order.
 template <int PASS>
-__global__ void __launch_bounds__(256) column_partial_kernel(const float* __restrict__ x, long long n_rows, int n_cols,
+__global__ void __launch_bounds__(512) column_partial_kernel(const float* __restrict__ x, long long n_rows, int n_cols,
                                                               long long row_stride, long long group_stride,
                                                               const double* __restrict__ shift,
                                                               double* __restrict__ partial)
@@ -114,7 +114,7 @@ __global__ void column_finish_kernel(const double* __restrict__ partial, int n_c
 // numpy array (EEG_VP_train_test.py:259-267) or a torch tensor, which scikit-learn converts to float64 before
 // `X -= mean_; X /= scale_` (train_semantic_predictor.py:47-48, eeg_text.py:142-144): the reference's result is the
 // float64 quotient, and this is its correctly rounded float32 value.
-__global__ void __launch_bounds__(256) standardize_kernel(const float* __restrict__ x, long long n_rows, int n_cols,
+__global__ void __launch_bounds__(512) standardize_kernel(const float* __restrict__ x, long long n_rows, int n_cols,
                                                            long long row_stride, long long group_stride,
                                                            const double* __restrict__ mean,
                                                            const double* __restrict__ scale, float* __restrict__ out)
@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(256) standardize_kernel(const float* __restric
   mean += static_cast<long long>(blockIdx.y) * n_cols;
   scale += static_cast<long long>(blockIdx.y) * n_cols;
   out += static_cast<long long>(blockIdx.y) * n_rows * n_cols;
-  // one row per block step, threads along the columns (no 64-bit division per element)
-  for (long long r = blockIdx.x; r < n_rows; r += gridDim.x) {
-    const float* xr = x + r * row_stride;
-    float* o = out + r * n_cols;
-    for (int c = threadIdx.x; c < n_cols; c += blockDim.x)
-      o[c] = static_cast<float>((static_cast<double>(xr[c]) - mean[c]) / scale[c]);
+  // threads along the columns (a thread keeps its column's mean / scale in registers), block steps over the rows:
+  // coalesced, no 64-bit division per element
+  for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+    const double m = mean[c], sc = scale[c];
+    for (long long r = blockIdx.x; r < n_rows; r += gridDim.x)
+      out[r * n_cols + c] = static_cast<float>((static_cast<double>(x[r * row_stride + c]) - m) / sc);
   }
 }
 
