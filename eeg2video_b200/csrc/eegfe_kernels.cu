@@ -5,9 +5,9 @@
 // window w at +50 w) and pulled into a ring of shared-memory slots with 1-D TMA bulk copies (cp.async.bulk ...
 // mbarrier::complete_tx, SASS UBLKCP), so neither the clip tensor nor the sliding-window tensor of the reference is
 // ever materialised.  One thread owns one channel-window (or one of its two sweeps): it reads its samples from shared
-// memory, runs the register-resident prime-factor FFT of bandpower.cuh in packed f32x2 arithmetic and contributes 5 PSD
-// + 5 DE values to a staged tile that leaves as linear, coalesced stores.  No tensor cores (FFT + reduction, no dense
-// contraction), no inter-CTA traffic.
+// memory, runs the register-resident prime-factor FFT of bandpower.cuh in packed f32x2 arithmetic and writes 5 PSD + 5 DE
+// values (500 ms kernel: straight from the lane; 1 s / 2 s kernel: through a staged tile that leaves as linear,
+// coalesced stores).  No tensor cores (FFT + reduction, no dense contraction), no inter-CTA traffic.
 //
 //   eegfe_stream.cuh   de_psd_stream_kernel   500 ms windows (sliding over clip rows, or pre-cut): FP32-pipe-bound;
 //                                             16 identical warps draw passes from a counter, tile duties fall to the

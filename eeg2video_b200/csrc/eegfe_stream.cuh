@@ -4,9 +4,8 @@
 // the FP32 pipe of the sub-partitions that host the producer warps partly idle: warps land on the four SM
 // sub-partitions round-robin, and with 16 warps x 128 registers filling the register file a producer warp displaces a
 // worker.  In the first form of this kernel (2 CTAs x (7 workers + 1 producer)) that capped the pipe at 14/16
-// (ncu: 74 %).  Here every warp is a worker (16 x 32 x 128 registers = the whole file) and the two serial duties --
-// issuing the TMA copies of the next tile, writing a finished tile's features to HBM -- fall to whichever warp
-// happens to finish a tile last.
+// (ncu: 74 %).  Here every warp is a worker (16 x 32 x 128 registers = the whole file) and the one serial duty --
+// issuing the TMA copies of the next tile -- falls to whichever warp happens to finish a tile last.
 //
 // Structure.  A CTA owns tiles t = 0, 1, ... (global tile blockIdx.x + t * gridDim.x) of 16 rows; tile t lives in
 // ring slot t % S.  A tile holds 16 rows x 7 windows = 112 channel-windows = 7 HALF-PASSES of 16 lanes (the lane
@@ -16,16 +15,16 @@
 //
 //   per pass:   wait full[slot]                         (TMA bytes landed; mbarrier transaction count)
 //               one channel-window per lane, register FFT (bandpower.cuh)
+//               5 DE + 5 PSD per lane                   -> straight to HBM, [clip][window][channel][band]
 //               consumed[slot] += half-passes           -> the warp that completes the tile re-arms full[slot] and
 //                                                          issues the 16 bulk copies of tile t + S into the slot
-//               wait drained[slot] >= generation        (staging rows of the slot's previous tile written out;
-//                                                          true long before in practice)
-//               stage 5 DE + 5 PSD per lane             [window][row][band]
-//               staged[slot] += half-passes             -> the warp that completes the tile copies the staged tile
-//                                                          to HBM (linear runs, see store_tile) and bumps drained
+//
+// (EEGFE_DIRECT_STORE=0 builds the round-1 store path for comparison: results staged [window][row][band] per tile,
+//  a second counter `staged[slot]`, the warp that completes it copies the tile to HBM and bumps `drained[slot]`, which
+//  later stagers of the slot wait for.)
 //
 // No block-wide or group barrier exists after the prologue.  Progress: the oldest unfinished pass only ever waits
-// for copies / copy-outs triggered by strictly older passes.
+// for copies triggered by strictly older passes.
 #pragma once
 
 namespace eegfe {
