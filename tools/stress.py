@@ -74,10 +74,31 @@ def main():
                     lambda n: n)
     mean, std = glmnet_inputs.channel_stats(raw, None)
     scale = (1.0 / std).float().contiguous()
-    shift = (-mean / std).float().contiguous()
+    center = mean.float().contiguous()
     bad += run_case("glmnet inputs", max(10, args.launches // 3),
-                    lambda i: (ops.glmnet_inputs_from_raw(raw[:14 - (i % 3)], scale, shift)[:3], 14 - (i % 3)),
+                    lambda i: (ops.glmnet_inputs_from_raw(raw[:14 - (i % 3)], scale, center)[:3], 14 - (i % 3)),
                     lambda n: n * 200)
+    # rows TMA cannot fetch: the cp.async instantiations (8-byte rows: T = 104002, 4-byte rows: T = 104001), through the
+    # C ABI directly (ops.de_psd_from_raw re-aligns some of these shapes instead)
+    from eeg2video_b200 import _lib
+    lib = _lib.load()
+    for t_len in (104002, 104001):
+        odd = synth.synth_blocks(14, 77, device=dev, block_len=t_len)
+        for mode in ("500ms", "1s", "2s"):
+            mid = frontend.MODES[mode]
+            nwin = ops.WINDOWS_PER_CLIP[mid]
+
+            def make(i, odd=odd, mid=mid, nwin=nwin, t_len=t_len):
+                n = 14 - (i % 4)
+                de = torch.empty((n * 200, nwin, 62, 5), device=dev)
+                psd = torch.empty_like(de)
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                _lib.check(lib.eegfe_de_psd_from_raw(odd.data_ptr(), n, 62, t_len, odd.stride(0), odd.stride(1), mid,
+                                                     de.data_ptr(), psd.data_ptr(), status.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream))
+                return (de, psd), n
+            bad += run_case(f"from_raw {mode} T={t_len} (cp.async loader)", max(10, args.launches // 3), make,
+                            lambda n: n * 200)
     sys.exit(1 if bad else 0)
 
 
