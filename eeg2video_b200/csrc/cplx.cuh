@@ -5,7 +5,8 @@
 //    scalar broadcasts and per-half sign flips used below into operand modifiers (.LO_HI, .F32, .NP), so a
 //    complex add costs 1 issue slot, a multiply by a constant twiddle 2, a radix-5 butterfly 18.
 //    Measured on B200 (tools/microbench/pipes.cu): FFMA2 issues at 0.5/clk/SMSP = the same FP32 lane rate
-//    as scalar FFMA at half the issue slots, which is what leaves room for the shared-memory loads.
+//    as scalar FFMA with half the instructions and register operands; it holds the issue port for both cycles
+//    (FFMA2 + IADD3 pairs issue every 3.1 cycles), so a lane-operation costs one issue cycle either way.
 //  * scalar  (device with EEGFE_PACKED=0, and the host build used ONLY by tests/hostemu): the same operations,
 //    in the same order, with explicitly rounded fp32 add / mul / fma, so both backends -- and the CPU
 //    emulation -- produce bit-identical band energies.
