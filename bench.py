@@ -868,6 +868,17 @@ def run_gpu_arm(args):
                      "frac": fp_ach / fp_peak, "lane_ops_per_channel_window": FP32_LANE_OPS_PER_CW[mode],
                      "window": fp_window,
                      "peak_source": f"148 SMs x 128 lanes x {sm_mhz:.0f} MHz (median SM clock sampled over the same window)"}
+        # the bound that actually binds the 500 ms kernel: the sub-partition's issue port -- a packed f32x2
+        # instruction holds it for two cycles, anything else for one.  Instruction counts per window-warp come from the
+        # committed ncu capture (profiles/ncu_r02_500ms.txt: smsp__inst_executed.sum / window-warps); cycles from this run.
+        issue_model = None
+        if mode == "500ms":
+            inst, packed = 2014.0, 981.0
+            cycles = fp_ms * 1e-3 * sm_mhz * 1e6 * 148 * 4 / (cw_step_gpu / 32.0)
+            issue_model = {"instructions_per_window_warp": inst, "packed_f32x2_per_window_warp": packed,
+                           "issue_cycles_per_window_warp": inst + packed, "measured_cycles_per_window_warp": cycles,
+                           "frac": (inst + packed) / cycles, "window": fp_window,
+                           "note": "issue-port occupancy of the 500 ms kernel; the arithmetic core alone needs 2539 cycles"}
         if sustained is not None:
             sus_gbs = sustained["value"] / world * BYTES_PER_CW[mode] / 1e9
             sustained["hbm_gbs_per_gpu"] = sus_gbs
@@ -902,7 +913,7 @@ def run_gpu_arm(args):
                     "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
                             "D2H of DE+PSD, 3 streams) -> pinned host features"},
             "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),
-            "roofline": roofline, "fp32_pipe": fp32_pipe, "single_subject": single, "other_modes": other_modes, "next_rows": next_rows,
+            "roofline": roofline, "fp32_pipe": fp32_pipe, "issue_model": issue_model, "single_subject": single, "other_modes": other_modes, "next_rows": next_rows,
             "cpu_baseline": cpu,
             "parity": parity,
         }
