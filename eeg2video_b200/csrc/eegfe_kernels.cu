@@ -47,6 +47,8 @@ struct Job {
   long long ch_stride;    // elements between channel rows of one unit
   unsigned d1, d2;
   unsigned n_ch;
+  unsigned n_ch_magic;    // min(floor(2^32 / n_ch), 2^32 - 1): __umulhi(g, magic) is floor(g / n_ch) or one less
+  unsigned d1_magic, d2_magic;   // the same for d1 and d2 (set by launch<>; used by the streaming kernel's hot paths)
   long long t_extent;     // valid elements of a channel row (tensor-map bound of the time axis); 0 = unknown
   int row_align;            // bytes every row start is a multiple of: 16 (TMA bulk copies), else 8 or 4 (cp.async loader)
   unsigned tiles_per_clip;  // > 0: tiles never straddle clips (tile = kRows channels of one clip), fetched as tensor boxes
@@ -181,6 +183,29 @@ __device__ __forceinline__ long long row_offset(const Job& job, unsigned g, int 
   const unsigned c = rem / job.d2;
   const unsigned r = rem - c * job.d2;
   if (out_base) *out_base = static_cast<int>((u * n_windows * job.n_ch + ch) * 5u);
+  return job.base + static_cast<long long>(q) * job.s0 + static_cast<long long>(c) * job.s1 +
+         static_cast<long long>(r) * job.s2 + static_cast<long long>(ch) * job.ch_stride;
+}
+
+// q = floor(g / d), r = g - q d without a hardware division: multiply-high by floor(2^32 / d) is q or q - 1
+__device__ __forceinline__ unsigned div_magic(unsigned g, unsigned d, unsigned magic, unsigned& r)
+{
+  unsigned q = __umulhi(g, magic);
+  r = g - q * d;
+  if (r >= d) {
+    r -= d;
+    ++q;
+  }
+  return q;
+}
+
+// row_offset() for the kernels whose Job carries the magic numbers (launch<>): same result, a third of the instructions
+__device__ __forceinline__ long long row_offset_fast(const Job& job, unsigned g)
+{
+  unsigned ch, rem, r;
+  const unsigned u = div_magic(g, job.n_ch, job.n_ch_magic, ch);
+  const unsigned q = div_magic(u, job.d1, job.d1_magic, rem);
+  const unsigned c = div_magic(rem, job.d2, job.d2_magic, r);
   return job.base + static_cast<long long>(q) * job.s0 + static_cast<long long>(c) * job.s1 +
          static_cast<long long>(r) * job.s2 + static_cast<long long>(ch) * job.ch_stride;
 }
@@ -894,6 +919,15 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
   job.tiles_per_clip = 0;
   job.rows_tma = 0;
   job.row_align = 16;
+  {
+    auto magic = [](unsigned d) {
+      const unsigned long long m = (1ull << 32) / (d ? d : 1u);
+      return m > 0xffffffffull ? 0xffffffffu : static_cast<unsigned>(m);
+    };
+    job.n_ch_magic = magic(job.n_ch);
+    job.d1_magic = magic(job.d1);
+    job.d2_magic = magic(job.d2);
+  }
   unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (!aligned16 && job.norm_out == nullptr) {
     // rows that are only 8- / 4-byte aligned: the same kernels with their cp.async loader instead of TMA bulk copies

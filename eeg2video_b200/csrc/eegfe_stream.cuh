@@ -172,7 +172,7 @@ __device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot,
       bulk_copy_g2s(slot, job.in + job.base + static_cast<long long>(row0) * SC::kLoad, nrows * SC::kRowBytes, bar);
   } else {
     for (int r = lane; r < nrows; r += 32) {
-      const long long off = row_offset(job, row0 + r, SC::kWindows, nullptr);
+      const long long off = row_offset_fast(job, row0 + r);
       bulk_copy_g2s(slot + r * SC::kRowStride, job.in + off, SC::kRowBytes, bar);
     }
   }
@@ -339,16 +339,20 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
       }
     }
     asm volatile("" : "+r"(pass));                        // everything below is recomputed from `pass` alone
-    locate();
     if constexpr (C::kDirectStore) {
       if (live) {
         // features [clip][window][channel][band]: this lane's ten values go straight out.  The 16 lanes of a half-pass
         // cover runs of 8 (lane-mapped tiles) or 16 consecutive channels of one window, i.e. 160 / 320 contiguous bytes
         // per array; the five 4-byte stores of a lane hit the same sectors back to back and merge in L2.
-        const unsigned g = tile_row0(t) + static_cast<unsigned>(meta >> 25);
-        const unsigned u = g / job.n_ch;
-        const unsigned ch = g - u * job.n_ch;
-        const unsigned w = C::kWindows == 1 ? 0u : static_cast<unsigned>((meta >> 14) & 0x7ff) / (5u * C::kRows);
+        // (Only the tile and the lane's (row, window) are re-derived here -- `live` implies a valid half-pass -- and
+        // g / n_ch is a multiply-high with one correction step: every instruction costs an issue cycle)
+        const unsigned h = 2 * pass + (lane >> 4);
+        const unsigned tt = h / C::kHalfPasses;
+        const int mm = *reinterpret_cast<volatile int*>(unit_meta + static_cast<int>(h - tt * C::kHalfPasses) * 16 + (lane & 15));
+        const unsigned g = tile_row0(tt) + static_cast<unsigned>(mm >> 25);
+        unsigned ch;
+        const unsigned u = div_magic(g, job.n_ch, job.n_ch_magic, ch);
+        const unsigned w = C::kWindows == 1 ? 0u : static_cast<unsigned>((mm >> 14) & 0x7ff) / (5u * C::kRows);
         const long long o = (static_cast<long long>(u * C::kWindows + w) * job.n_ch + ch) * 5;
 #pragma unroll
         for (int b = 0; b < 5; ++b) {
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
         }
       }
     } else {
+      locate();
       if (live) {
         // staging rows of the slot's previous tile must have been written out (true long before, in practice)
         while (ld_acquire_smem(&drained[s]) < gen) __nanosleep(32);
