@@ -314,10 +314,12 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
 #include "eegfe_stream.cuh"
 namespace eegfe {
 
-// Ring-kernel producer, rows that are only 8- / 4-byte aligned (an odd block length or stride): cp.async instead of TMA
-// bulk copies, one row per step, lanes side by side; the phase completes when this warp's copies have landed.
+// Ring-kernel producer of the SMALL instantiation -- rows that are only 8- / 4-byte aligned (an odd block length or
+// stride): cp.async instead of TMA bulk copies, one row per step, lanes side by side; the phase completes when this
+// warp's copies have landed.  A kernel of its own, like the streaming kernel's: the TMA kernels carry none of this code
+// (an out-of-line call to it from inside the TMA streaming kernel hung that kernel on B200).
 template <class C>
-__device__ __noinline__ void ring_load_tile_small(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
+__device__ __forceinline__ void ring_load_tile_small(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
                                                   unsigned generation, unsigned row0, unsigned nrows)
 {
   const Job& job = *jobp;
@@ -357,7 +359,7 @@ __device__ __noinline__ void ring_load_tile_small(const Job* jobp, float* slot, 
 //              the epilogue (the same additions as the one-thread form, so the results are bit-identical).
 // kSplit == 1: a worker runs both sweeps and the epilogue and stages (de, psd).
 // ---------------------------------------------------------------------------------------------------------------
-template <class C>
+template <class C, bool SMALL = false>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const __grid_constant__ Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < C::kSlots; ++s) {
-      mbar_init(&full_bar[s], full_barrier_arrivals(job));
+      mbar_init(&full_bar[s], SMALL ? 32 : 1);
       mbar_init(&empty_bar[s], C::kGroupWarps);
       armed[s] = 0;
     }
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
         __syncwarp();
         continue;
       }
-      if (job.row_align < 16) {            // cold path, out of line (cp.async instead of TMA bulk copies)
+      if constexpr (SMALL) {               // cp.async instead of TMA bulk copies
         ring_load_tile_small<C>(&job, ring + s * C::kSlotFloats, &full_bar[s], &armed[s],
                                 static_cast<unsigned>(m / C::kSlots), row0, nrows);
         continue;
@@ -953,9 +955,16 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
       unsigned grid = persistent_grid(static_cast<unsigned>(sm_count()) * C::kCtasPerSm);
       if (grid > n_tiles) grid = n_tiles;
       static std::atomic<unsigned long long> configured{0};
-      const int rc = configure_smem(configured, de_psd_kernel<C>, C::kSmemBytes);
-      if (rc != 0) return rc;
-      de_psd_kernel<C><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+      if (job.row_align < 16) {
+        static std::atomic<unsigned long long> configured_small{0};
+        const int rc = configure_smem(configured_small, de_psd_kernel<C, true>, C::kSmemBytes);
+        if (rc != 0) return rc;
+        de_psd_kernel<C, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+      } else {
+        const int rc = configure_smem(configured, de_psd_kernel<C>, C::kSmemBytes);
+        if (rc != 0) return rc;
+        de_psd_kernel<C><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+      }
     }
   } else {
     return EEGFE_EINVAL;                     // the normalised-clip product needs 16-byte aligned rows

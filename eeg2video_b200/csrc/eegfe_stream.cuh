@@ -118,10 +118,6 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
 {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrivals that complete a phase of a slot's `full` barrier: 1 (arrive.expect_tx by the lane that issues the TMA copies)
-// or, for rows TMA cannot fetch, the 32 lanes of the warp that issues the cp.async copies
-__device__ __forceinline__ unsigned full_barrier_arrivals(const Job& job) { return job.row_align < 16 ? 32u : 1u; }
-
 // Rows that are only 8- or 4-byte aligned (job.row_align; an odd block length or stride) cannot ride on TMA bulk copies:
 // the SMALL instantiation of the kernel fetches them with 8- / 4-byte cp.async (LDGSTS), one row per step, lanes side
 // by side; every lane's arrival on the slot's barrier (32 per phase in this instantiation) fires when its copies have
