@@ -359,7 +359,7 @@ __device__ __forceinline__ void ring_load_tile_small(const Job* jobp, float* slo
 //              the epilogue (the same additions as the one-thread form, so the results are bit-identical).
 // kSplit == 1: a worker runs both sweeps and the epilogue and stages (de, psd).
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, bool SMALL = false>
+template <class C, bool SMALL = false, bool TENSOR = false>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const __grid_constant__ Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -380,8 +380,10 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   const int lane = tid & 31;
   // Tiles: kRows consecutive rows -- or, with job.tiles_per_clip (tensor-copy producer), kRows consecutive CHANNELS
   // of one clip, so that a tile is a rectangle of the (time, channel, block) tensor; a clip's last tile is short.
-  // rows that fit one tensor box (inner extent <= 256); compiled into the 2 s instantiation only (measurement option)
-  constexpr bool kTensorLoads = (C::kLoad == 200 && C::kHann == kHannTwoSec);
+  // TENSOR: tiles fetched by one TMA tensor copy each (rows that fit one box, inner extent <= 256) -- an instantiation
+  // of its own (measurement option, eegfe_set_tensor_loads), so that the default kernels carry none of its code
+  constexpr bool kTensorLoads = TENSOR;
+  static_assert(!TENSOR || (C::kLoad == 200 && C::kHann == kHannTwoSec && !SMALL), "tensor boxes: the 2 s shape only");
   const unsigned tpc = kTensorLoads ? job.tiles_per_clip : 0u;
   const unsigned n_tiles = tpc ? (job.total_rows / job.n_ch) * tpc : (job.total_rows + C::kRows - 1) / C::kRows;
   // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -955,7 +957,14 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
       unsigned grid = persistent_grid(static_cast<unsigned>(sm_count()) * C::kCtasPerSm);
       if (grid > n_tiles) grid = n_tiles;
       static std::atomic<unsigned long long> configured{0};
-      if (job.row_align < 16) {
+      if (job.tiles_per_clip != 0 || job.rows_tma != 0) {
+        if constexpr (C::kLoad == 200 && C::kHann == kHannTwoSec) {
+          static std::atomic<unsigned long long> configured_tensor{0};
+          const int rc = configure_smem(configured_tensor, de_psd_kernel<C, false, true>, C::kSmemBytes);
+          if (rc != 0) return rc;
+          de_psd_kernel<C, false, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+        }
+      } else if (job.row_align < 16) {
         static std::atomic<unsigned long long> configured_small{0};
         const int rc = configure_smem(configured_small, de_psd_kernel<C, true>, C::kSmemBytes);
         if (rc != 0) return rc;
