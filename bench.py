@@ -873,7 +873,7 @@ def run_gpu_arm(args):
         # committed ncu capture (profiles/ncu_r02_500ms.txt: smsp__inst_executed.sum / window-warps); cycles from this run.
         issue_model = None
         if mode == "500ms":
-            inst, packed = 2014.0, 981.0
+            inst, packed = 1990.0, 982.0
             cycles = fp_ms * 1e-3 * sm_mhz * 1e6 * 148 * 4 / (cw_step_gpu / 32.0)
             issue_model = {"instructions_per_window_warp": inst, "packed_f32x2_per_window_warp": packed,
                            "issue_cycles_per_window_warp": inst + packed, "measured_cycles_per_window_warp": cycles,
