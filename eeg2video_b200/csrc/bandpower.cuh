@@ -69,11 +69,14 @@ constexpr int w8_im_code(int d) { constexpr int t[8] = {0, -2, -1, -2, 0, 2, 1, 
 // ---- window samples ------------------------------------------------------------------------------------------
 // Samples are fetched as aligned vectors (identical addresses are merged by the compiler):
 //   VEC = 2: float2 / LDS.64 -- sliding 500 ms windows start at multiples of 50 floats, i.e. only 8-byte aligned;
-//   VEC = 4: float4 / LDS.128 -- 1 s / 2 s / pre-cut windows start 16-byte aligned.
+//   VEC = 4: float4 / LDS.128 -- 1 s / 2 s / pre-cut windows start 16-byte aligned;
+//   VEC = 1: scalar loads -- rows that sit 4, 8 or 12 bytes into their shared-memory row (ring kernel, SHIFT form).
 template <int N, int VEC>
 EEGFE_FN float sample(const float* win)
 {
-  if constexpr (VEC == 4) {
+  if constexpr (VEC == 1) {
+    return win[N];
+  } else if constexpr (VEC == 4) {
     const float4 p = *reinterpret_cast<const float4*>(win + (N & ~3));
     return (N & 3) == 0 ? p.x : (N & 3) == 1 ? p.y : (N & 3) == 2 ? p.z : p.w;
   } else {

@@ -50,7 +50,8 @@ struct Job {
   unsigned n_ch_magic;    // min(floor(2^32 / n_ch), 2^32 - 1): __umulhi(g, magic) is floor(g / n_ch) or one less
   unsigned d1_magic, d2_magic;   // the same for d1 and d2 (set by launch<>; used by the streaming kernel's hot paths)
   long long t_extent;     // valid elements of a channel row (tensor-map bound of the time axis); 0 = unknown
-  int row_align;            // bytes every row start is a multiple of: 16 (TMA bulk copies), else 8 or 4 (cp.async loader)
+  int row_align;            // bytes every row start is a multiple of: 16 (TMA bulk copies of the rows themselves), else 8
+                            // or 4 (streaming kernel: cp.async loader; ring kernel: TMA copies of the aligned span, SHIFT)
   unsigned tiles_per_clip;  // > 0: tiles never straddle clips (tile = kRows channels of one clip), fetched as tensor boxes
   int rows_tma;             // pre-cut windows in a dense / uniformly strided 2-D array: tile = tensor box of kRows rows
   // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = (x - mean[ch]) * scale[ch]
@@ -314,36 +315,8 @@ __device__ __forceinline__ void unit_to_row_window(int unit, int& row, int& w)
 #include "eegfe_stream.cuh"
 namespace eegfe {
 
-// Ring-kernel producer of the SMALL instantiation -- rows that are only 8- / 4-byte aligned (an odd block length or
-// stride): cp.async instead of TMA bulk copies, one row per step, lanes side by side; the phase completes when this
-// warp's copies have landed.  A kernel of its own, like the streaming kernel's: the TMA kernels carry none of this code
-// (an out-of-line call to it from inside the TMA streaming kernel hung that kernel on B200).
-template <class C>
-__device__ __forceinline__ void ring_load_tile_small(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
-                                                  unsigned generation, unsigned row0, unsigned nrows)
-{
-  const Job& job = *jobp;
-  const int lane = threadIdx.x & 31;
-  if (lane == 0) st_release_smem(armed, generation + 1u);
-#pragma unroll 1
-  for (unsigned r = 0; r < nrows; ++r) {
-    const float* src = job.in + row_offset(job, row0 + r, C::kWindows, nullptr);
-    float* dst = slot + r * C::kRowStride;
-    if (job.row_align == 8) {
-#pragma unroll 1
-      for (int i = 2 * lane; i < C::kLoad; i += 64) cp_async_small<8>(dst + i, src + i);
-    } else {
-#pragma unroll 1
-      for (int i = lane; i < C::kLoad; i += 32) cp_async_small<4>(dst + i, src + i);
-    }
-  }
-  cp_async_arrive(bar);
-  __syncwarp();
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// the ring kernel (rows 16-byte aligned; 1 s / 2 s modes, pre-cut 1 s windows): warp-specialised, no block-wide
-// barrier in the steady state
+// the ring kernel (1 s / 2 s modes, pre-cut 1 s windows): warp-specialised, no block-wide barrier in the steady state
 //
 // A CTA walks its tiles m = 0, 1, 2, ... (global tile blockIdx.x + m * gridDim.x).  Tile m lands in ring slot
 // m % kSlots and is processed by worker group m % kGroups.
@@ -358,8 +331,15 @@ __device__ __forceinline__ void ring_load_tile_small(const Job* jobp, float* slo
 // kSplit == 2: even-sweep warps and odd-sweep warps stage their partial band energies; store_tile adds them and does
 //              the epilogue (the same additions as the one-thread form, so the results are bit-identical).
 // kSplit == 1: a worker runs both sweeps and the epilogue and stages (de, psd).
+//
+// SHIFT (rows that are only 4- or 8-byte aligned: an odd block length or stride): TMA cannot start a copy there, but
+// it can fetch the 16-byte aligned span AROUND the row -- from the row start rounded down to the row end rounded up,
+// at most 16 bytes more, which is exactly the slot's row padding -- so the row lands k = 0..3 floats into its
+// shared-memory row.  The producer notes k per row, the worker adds it to its window pointer and reads scalar
+// (LDS.32) instead of LDS.128.  Same HBM traffic and copy count as the aligned kernel, no second pass.  The span stays
+// inside the caller's allocation as long as that starts and ends on 16-byte boundaries (cudaMalloc, torch: always).
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, bool SMALL = false, bool TENSOR = false>
+template <class C, bool SHIFT = false, bool TENSOR = false>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const __grid_constant__ Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -375,6 +355,9 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   // independently, so a group can reach tile m before the slot's previous tile (m - kSlots, another group's unless
   // kSlots % kGroups == 0) has even been requested.  Waiting for armed[s] > k first makes the parity wait unambiguous.
   __shared__ unsigned armed[C::kSlots];
+  __shared__ unsigned char row_shift[SHIFT ? C::kSlots : 1][SHIFT ? C::kRows : 1];   // k of every row in flight
+  static_assert(!SHIFT || (C::kRowStride >= C::kLoad + 4 && C::kRows <= 32), "a shifted row needs 16 bytes of padding");
+  constexpr int kVec = SHIFT ? 1 : C::kVec;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -383,7 +366,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   // TENSOR: tiles fetched by one TMA tensor copy each (rows that fit one box, inner extent <= 256) -- an instantiation
   // of its own (measurement option, eegfe_set_tensor_loads), so that the default kernels carry none of its code
   constexpr bool kTensorLoads = TENSOR;
-  static_assert(!TENSOR || (C::kLoad == 200 && C::kHann == kHannTwoSec && !SMALL), "tensor boxes: the 2 s shape only");
+  static_assert(!TENSOR || (C::kLoad == 200 && C::kHann == kHannTwoSec && !SHIFT), "tensor boxes: the 2 s shape only");
   const unsigned tpc = kTensorLoads ? job.tiles_per_clip : 0u;
   const unsigned n_tiles = tpc ? (job.total_rows / job.n_ch) * tpc : (job.total_rows + C::kRows - 1) / C::kRows;
   // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -410,7 +393,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < C::kSlots; ++s) {
-      mbar_init(&full_bar[s], SMALL ? 32 : 1);
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], C::kGroupWarps);
       armed[s] = 0;
     }
@@ -447,9 +430,26 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
         __syncwarp();
         continue;
       }
-      if constexpr (SMALL) {               // cp.async instead of TMA bulk copies
-        ring_load_tile_small<C>(&job, ring + s * C::kSlotFloats, &full_bar[s], &armed[s],
-                                static_cast<unsigned>(m / C::kSlots), row0, nrows);
+      if constexpr (SHIFT) {
+        // the aligned span around every row (kRows <= 32: one row per lane)
+        const float* src = nullptr;
+        unsigned bytes = 0;
+        if (lane < nrows) {
+          const float* p = job.in + row_offset(job, row0 + lane, C::kWindows, nullptr);
+          const unsigned k = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) >> 2) & 3u;
+          row_shift[s][lane] = static_cast<unsigned char>(k);
+          src = p - k;
+          bytes = ((k + C::kLoad) * 4u + 15u) & ~15u;
+        }
+        const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+        __syncwarp();                                              // row_shift[] is written before lane 0 arrives
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], total);
+          st_release_smem(&armed[s], static_cast<unsigned>(m / C::kSlots) + 1u);
+        }
+        __syncwarp();
+        if (lane < nrows) bulk_copy_g2s(ring + s * C::kSlotFloats + lane * C::kRowStride, src, bytes, &full_bar[s]);
+        __syncwarp();
         continue;
       }
       if (lane == 0) {
@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       const int meta = *reinterpret_cast<volatile int*>(thread_meta + tid);
       const bool live = (meta >> 25) < nrows;
       const float* win = ring + s * C::kSlotFloats + (meta & 0x3fff);
+      if constexpr (SHIFT) win += live ? row_shift[s][meta >> 25] : 0;
       float va[5], vb[5];
 #ifdef EEGFE_NOCOMPUTE      // (measurement builds only: the memory pipeline without the FFT -- one sample per window)
       if (live) {
@@ -491,11 +492,11 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
       if (live) {
         if constexpr (C::kSplit == 1) {
           float e[5];
-          window_band_energy<C::kNi, C::kHann, C::kVec>(win, e);
+          window_band_energy<C::kNi, C::kHann, kVec>(win, e);
           if (band_features(e, vb, va) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
         } else {
           const float zero5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-          sweep_any<C::kNi, C::kHann, C::kVec>(win, sweep, zero5, va);
+          sweep_any<C::kNi, C::kHann, kVec>(win, sweep, zero5, va);
         }
       }
 #endif
@@ -934,7 +935,8 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
   }
   unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (!aligned16 && job.norm_out == nullptr) {
-    // rows that are only 8- / 4-byte aligned: the same kernels with their cp.async loader instead of TMA bulk copies
+    // rows that are only 8- / 4-byte aligned: the streaming kernel with its cp.async loader, the ring kernel with TMA
+    // copies of the 16-byte aligned span around each row (SHIFT instantiation)
     const bool even = reinterpret_cast<uintptr_t>(job.in) % 8 == 0 && job.base % 2 == 0 && job.s0 % 2 == 0 &&
                       job.s1 % 2 == 0 && job.s2 % 2 == 0 && job.ch_stride % 2 == 0;
     job.row_align = even ? 8 : 4;
@@ -965,8 +967,8 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
           de_psd_kernel<C, false, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
         }
       } else if (job.row_align < 16) {
-        static std::atomic<unsigned long long> configured_small{0};
-        const int rc = configure_smem(configured_small, de_psd_kernel<C, true>, C::kSmemBytes);
+        static std::atomic<unsigned long long> configured_shift{0};
+        const int rc = configure_smem(configured_shift, de_psd_kernel<C, true>, C::kSmemBytes);
         if (rc != 0) return rc;
         de_psd_kernel<C, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
       } else {

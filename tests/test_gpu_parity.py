@@ -418,6 +418,44 @@ def test_unaligned_block_length_uses_fallback_loader():
     assert torch.equal(de, de_a) and torch.equal(psd, psd_a)
 
 
+@pytest.mark.parametrize("mode", ("500ms", "1s", "2s"))
+@pytest.mark.parametrize("t_len,offset", ((104001, 0), (104002, 0), (104003, 0), (104003, 1), (104002, 2), (104001, 3)))
+def test_rows_of_every_alignment(mode, t_len, offset):
+    """Rows that start 4, 8 or 12 bytes off a 16-byte boundary -- an odd block length (the offset then changes from
+    row to row) or a view that starts inside a buffer of pitch 104004 (the same offset for every row).  TMA cannot start a copy there:
+    the ring kernel (1 s / 2 s) copies the aligned span around each row and reads it shifted, the streaming kernel
+    (500 ms) falls back to cp.async.  Called through the C ABI directly and through the op (which re-aligns 4-byte rows
+    in 500 ms mode); all must equal the result on an aligned copy, bit for bit.  37 channels: ragged tiles."""
+    base = synth.synth_blocks(1, 9, device=DEV, channels=37, block_len=t_len + offset)
+    raw = base[..., offset:]
+    assert raw.data_ptr() % 16 == 4 * offset
+    aligned = raw[..., :104000].contiguous()
+    want = ops.de_psd_from_raw(aligned, frontend.MODES[mode])
+    got = ops.de_psd_from_raw(raw, frontend.MODES[mode])
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    de, psd = torch.zeros_like(want[0]), torch.zeros_like(want[1])
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    before = _lib.launch_count()
+    _lib.check(_lib.load().eegfe_de_psd_from_raw(raw.data_ptr(), raw.shape[0], raw.shape[1], raw.shape[2], raw.stride(0),
+                                                 raw.stride(1), frontend.MODES[mode], de.data_ptr(), psd.data_ptr(),
+                                                 status.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert _lib.launch_count() == before + 1                                   # one kernel, no re-alignment pass
+    assert torch.equal(de, want[0]) and torch.equal(psd, want[1]) and int(status.item()) == 0
+
+
+def test_shifted_rows_at_the_end_of_an_allocation():
+    """The aligned span around the LAST row of a buffer ends at most 12 bytes past the row -- inside the allocation,
+    whose size is a multiple of 16 bytes: a recording that fills its allocation exactly, last rows included."""
+    n_ch, t_len = 62, 104001
+    flat = torch.empty(2 * n_ch * t_len, device=DEV)                           # torch rounds the block up, not down
+    raw = flat.view(2, n_ch, t_len)
+    raw.copy_(synth.synth_blocks(2, 13, device=DEV, channels=n_ch, block_len=t_len))
+    for mode in ("1s", "2s"):
+        want = ops.de_psd_from_raw(raw[..., :104000].contiguous(), frontend.MODES[mode])
+        got = ops.de_psd_from_raw(raw, frontend.MODES[mode])
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
 # ---- host pipeline / compact layout -----------------------------------------------------------------------------------
 def test_from_concepts_equals_from_raw(subject):
     raw, _ = subject

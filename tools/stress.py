@@ -78,8 +78,9 @@ def main():
     bad += run_case("glmnet inputs", max(10, args.launches // 3),
                     lambda i: (ops.glmnet_inputs_from_raw(raw[:14 - (i % 3)], scale, center)[:3], 14 - (i % 3)),
                     lambda n: n * 200)
-    # rows TMA cannot fetch: the cp.async instantiations (8-byte rows: T = 104002, 4-byte rows: T = 104001), through the
-    # C ABI directly (ops.de_psd_from_raw re-aligns some of these shapes instead)
+    # rows TMA cannot start at (8-byte rows: T = 104002, 4-byte rows: T = 104001): the streaming kernel's cp.async
+    # instantiation and the ring kernel's shifted-span instantiation, through the C ABI directly
+    # (ops.de_psd_from_raw re-aligns 4-byte rows in 500 ms mode instead)
     from eeg2video_b200 import _lib
     lib = _lib.load()
     for t_len in (104002, 104001):
@@ -97,7 +98,7 @@ def main():
                                                      de.data_ptr(), psd.data_ptr(), status.data_ptr(),
                                                      torch.cuda.current_stream().cuda_stream))
                 return (de, psd), n
-            bad += run_case(f"from_raw {mode} T={t_len} (cp.async loader)", max(10, args.launches // 3), make,
+            bad += run_case(f"from_raw {mode} T={t_len} (rows TMA cannot start at)", max(10, args.launches // 3), make,
                             lambda n: n * 200)
     sys.exit(1 if bad else 0)
 
