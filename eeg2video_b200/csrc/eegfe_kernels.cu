@@ -824,11 +824,23 @@ static int launch_stream(const Job& job, cudaStream_t stream)
       return EEGFE_EINVAL;
     }
   } else if (job.row_align < 16) {
-    // rows TMA cannot fetch: the cp.async instantiation (a kernel of its own; the TMA kernel carries none of its code)
-    static std::atomic<unsigned long long> configured_small{0};
-    const int rc = configure_smem(configured_small, de_psd_stream_kernel<SC, false, true>, SC::kSmemBytes);
-    if (rc != 0) return rc;
-    de_psd_stream_kernel<SC, false, true><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
+    // rows TMA cannot start a copy at -- kernels of their own, the default kernel carries none of their code.
+    // Sliding 500 ms windows whose rows are 8-byte aligned (and padded in shared memory): TMA copies of the aligned
+    // span around each row, read shifted by 0 or 2 floats (still LDS.64).  Everything else -- 4-byte rows, pre-cut
+    // windows (dense rows, nothing to shift into) -- cp.async.
+    if (kCanNorm && job.row_align == 8) {
+      if constexpr (kCanNorm) {
+        static std::atomic<unsigned long long> configured_shift2{0};
+        const int rc = configure_smem(configured_shift2, de_psd_stream_kernel<SC, false, false, 2>, SC::kSmemBytes);
+        if (rc != 0) return rc;
+        de_psd_stream_kernel<SC, false, false, 2><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
+      }
+    } else {
+      static std::atomic<unsigned long long> configured_small{0};
+      const int rc = configure_smem(configured_small, de_psd_stream_kernel<SC, false, true>, SC::kSmemBytes);
+      if (rc != 0) return rc;
+      de_psd_stream_kernel<SC, false, true><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
+    }
   } else {
     const int rc = configure_smem(configured, de_psd_stream_kernel<SC, false>, SC::kSmemBytes);
     if (rc != 0) return rc;

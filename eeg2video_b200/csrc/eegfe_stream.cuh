@@ -147,9 +147,12 @@ __device__ __forceinline__ void stream_load_tile_small(const Job* jobp, float* s
 
 // whole warp: re-arm `bar` and issue the bulk copies of the tile starting at global row `row0`: one per row, or a
 // single one when the rows sit back to back in HBM exactly as they do in the slot (pre-cut windows, dense array).
-template <class SC, bool SMALL>
+// SHIFT != 0 (rows that are only 4- / 8-byte aligned): one copy per row of the 16-byte aligned span AROUND the row --
+// at most 16 bytes more than the row, the slot's row padding -- so that the row lands k = 0..3 floats into its
+// shared-memory row; k is noted per row in `shift` (published by lane 0's arrival on the barrier).
+template <class SC, bool SMALL, int SHIFT>
 __device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot, uint64_t* bar, unsigned* armed,
-                                                   unsigned generation, unsigned row0, int nrows)
+                                                   unsigned generation, unsigned row0, int nrows, unsigned char* shift)
 {
   if constexpr (SMALL) {
     stream_load_tile_small<SC>(jobp, slot, bar, armed, generation, row0, nrows);
@@ -158,6 +161,28 @@ __device__ EEGFE_STREAM_DUTY void stream_load_tile(const Job* jobp, float* slot,
   const Job& job = *jobp;
   const int lane = threadIdx.x & 31;
   fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy refill
+  if constexpr (SHIFT != 0) {
+    static_assert(SHIFT == 0 || (SC::kRows <= 32 && SC::kRowStride >= SC::kLoad + 4), "a shifted row needs 16 bytes of padding");
+    const float* src = nullptr;
+    unsigned bytes = 0;
+    if (lane < nrows) {
+      const float* p = job.in + row_offset_fast(job, row0 + lane);
+      const unsigned k = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) >> 2) & 3u;
+      shift[lane] = static_cast<unsigned char>(k);
+      src = p - k;
+      bytes = ((k + SC::kLoad) * 4u + 15u) & ~15u;
+    }
+    const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+    __syncwarp();                            // shift[] is written before lane 0 arrives
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, total);
+      st_release_smem(armed, generation + 1u);
+    }
+    __syncwarp();
+    if (lane < nrows) bulk_copy_g2s(slot + lane * SC::kRowStride, src, bytes, bar);
+    __syncwarp();
+    return;
+  }
   if (lane == 0) {
     mbar_arrive_expect_tx(bar, nrows * SC::kRowBytes);
     st_release_smem(armed, generation + 1u);            // see `armed` in the kernel
@@ -217,10 +242,19 @@ __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const flo
   }
 }
 
-template <class SC, bool NORM, bool SMALL = false>
+// SMALL: rows fetched with cp.async (rows that are only 4-byte aligned; pre-cut windows that are not 16-byte aligned:
+//        their rows have no padding to shift into).
+// SHIFT: rows fetched as the aligned span around them and read k floats in -- 2: every k is 0 or 2 (8-byte aligned
+//        rows), windows still read with LDS.64.  (1: any k, scalar LDS.32 -- compiles, and HANGS on B200 on every
+//        input, k = 0 included, while the same loader with LDS.64 reads and the same scalar reads in the ring kernel
+//        work; control flow of the two SASS listings is identical.  Not instantiated; cause not found.  DESIGN.md 4.1.)
+template <class SC, bool NORM, bool SMALL = false, int SHIFT = 0>
 __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __grid_constant__ Job job)
 {
   using C = SC;
+  static_assert(!(SMALL && SHIFT != 0) && !(NORM && SHIFT != 0), "one loader per instantiation; normalised clips need aligned rows");
+  constexpr int kVec = SHIFT == 1 ? 1 : C::kVec;
+  __shared__ unsigned char row_shift[SHIFT != 0 ? C::kSlots : 1][SHIFT != 0 ? C::kRows : 1];
   static_assert(!NORM || (C::kLoad == 400 && C::kWindows == 7), "normalised clips ride on the sliding 500 ms form");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const ring = reinterpret_cast<float*>(smem_raw);                     // [slot][row][kRowStride]
@@ -283,7 +317,8 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
     const unsigned w = tid >> 5;
     if (w < C::kSlots && w < n_mine) {
       const unsigned row0 = tile_row0(w);
-      stream_load_tile<C, SMALL>(&job, ring + w * C::kSlotFloats, &full_bar[w], &armed[w], 0u, row0, tile_nrows(row0));
+      stream_load_tile<C, SMALL, SHIFT>(&job, ring + w * C::kSlotFloats, &full_bar[w], &armed[w], 0u, row0,
+                                        tile_nrows(row0), row_shift[SHIFT != 0 ? w : 0]);
     }
   }
 
@@ -330,7 +365,9 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
       }
       if (live) {
         float e[5];
-        window_band_energy<4, kHannHalfSec, C::kVec>(ring + s * C::kSlotFloats + (meta & 0x3fff), e);
+        const float* win = ring + s * C::kSlotFloats + (meta & 0x3fff);
+        if constexpr (SHIFT != 0) win += row_shift[s][meta >> 25];
+        window_band_energy<4, kHannHalfSec, kVec>(win, e);
         if (band_features(e, psd, de) && job.status != nullptr) atomicOr(job.status, EEGFE_STATUS_ZERO_POWER);
       }
     }
@@ -391,8 +428,8 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
       if (last & 1u) {
         if (tk + C::kSlots < n_mine) {
           const unsigned r0 = tile_row0(tk + C::kSlots);
-          stream_load_tile<C, SMALL>(&job, ring + sk * C::kSlotFloats, &full_bar[sk], &armed[sk], tk / C::kSlots + 1, r0,
-                              tile_nrows(r0));
+          stream_load_tile<C, SMALL, SHIFT>(&job, ring + sk * C::kSlotFloats, &full_bar[sk], &armed[sk],
+                                            tk / C::kSlots + 1, r0, tile_nrows(r0), row_shift[SHIFT != 0 ? sk : 0]);
         }
       }
       if constexpr (!C::kDirectStore) {

@@ -50,15 +50,13 @@ def de_psd_from_raw(raw: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.T
         de = torch.empty((n_blocks * 200, n_win, n_ch, 5), dtype=torch.float32, device=raw.device)
         psd = torch.empty_like(de)
         status = torch.zeros(1, dtype=torch.int32, device=raw.device)
-        aligned = raw.data_ptr() % 16 == 0 and raw.stride(0) % 4 == 0 and raw.stride(1) % 4 == 0
-        even = raw.data_ptr() % 8 == 0 and raw.stride(0) % 2 == 0 and raw.stride(1) % 2 == 0
         # Rows that are not 16-byte aligned (an odd block length or stride) cannot be the source of a TMA bulk copy.
-        # 1 s / 2 s modes: libeegfe copies the 16-byte aligned span around each row instead and reads it shifted
-        # (ring kernel, SHIFT form) -- no extra pass.  500 ms mode: the streaming kernel fetches such rows with 8- / 4-byte
-        # cp.async, measured on B200 (24 subjects) at 6.4 / 4.9 G channel-windows/s against 5.8 G for re-aligning the clips
-        # first (one extra HBM pass through a bounded scratch buffer) and running the TMA kernel -- so 8-byte rows go
-        # straight in and 4-byte rows are re-aligned.
-        if aligned or mode != _lib.MODE_500MS or even or n_blocks == 0 or t_len < 40 * 2600:
+        # libeegfe then copies the 16-byte aligned span around each row and reads it shifted (1 s / 2 s modes; 500 ms
+        # mode when the rows are 8-byte aligned) -- one launch, no extra pass.  500 ms mode with 4-byte rows: the library's
+        # cp.async loader manages 4.9 G channel-windows/s (measured, 24 subjects) against 5.8 G for re-aligning the clips
+        # first (one extra HBM pass through a bounded scratch buffer) and running the TMA kernel, so that is done here.
+        even = raw.data_ptr() % 8 == 0 and raw.stride(0) % 2 == 0 and raw.stride(1) % 2 == 0
+        if mode != _lib.MODE_500MS or even or n_blocks == 0 or t_len < 40 * 2600:
             _lib.check(lib.eegfe_de_psd_from_raw(
                 raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), mode,
                 de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
