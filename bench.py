@@ -610,6 +610,8 @@ def run_gpu_arm(args):
     # ---- end to end: pinned host recordings -> H2D -> fused kernel -> D2H of the features, every step ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     numa_cpus = pipeline.bind_to_gpu_numa_node(dev) if world > 1 else None     # node-local pinned buffers per rank
+    # compact="auto": the pipeline times the strided (live samples only) and the contiguous (whole rows) upload of its
+    # first chunk during the warm-up run and keeps the faster -- which one wins differs from host to host
     pipe = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode)
     raw_host = torch.empty((S * 7, 62, 104000), dtype=torch.float32).pin_memory()
     raw_host.copy_(raw)
@@ -653,21 +655,24 @@ def run_gpu_arm(args):
             psd_host.copy_(psd_buf, non_blocking=True)
     torch.cuda.synchronize()
     h2d_ceiling_duplex = 2 * raw_host.numel() * 4 / max_over_ranks(time.perf_counter() - t0) / 1e9
-    pipe_c = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode, compact=False)
-    de_host.zero_()
-    psd_host.zero_()
-    pipe_c.run(raw_host, de_host, psd_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_layouts = {}
+    for layout_name, layout_compact in (("contiguous_upload", False), ("strided_upload", True)):
+        pipe_c = pipeline.HostPipeline(dev, 62, 104000, chunk_blocks=args.chunk_blocks, mode=mode, compact=layout_compact)
+        de_host.zero_()
+        psd_host.zero_()
         pipe_c.run(raw_host, de_host, psd_host)
-    torch.cuda.synchronize()
-    e2e_c_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_contig = {"value": world * cw_step_gpu * e2e_steps / e2e_c_s, "unit": UNIT,
-                  "h2d_bytes_per_step": int(pipe_c.h2d_bytes(S * 7)),
-                  "h2d_gbs_per_gpu": pipe_c.h2d_bytes(S * 7) / (e2e_c_s / e2e_steps) / 1e9,
-                  "matches_device_result": max_over_ranks(0.0 if torch.equal(de_host, de_buf.cpu()) else 1.0) == 0.0}
-    del pipe_c
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pipe_c.run(raw_host, de_host, psd_host)
+        torch.cuda.synchronize()
+        e2e_c_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_layouts[layout_name] = {
+            "value": world * cw_step_gpu * e2e_steps / e2e_c_s, "unit": UNIT,
+            "h2d_bytes_per_step": int(pipe_c.h2d_bytes(S * 7)),
+            "h2d_gbs_per_gpu": pipe_c.h2d_bytes(S * 7) / (e2e_c_s / e2e_steps) / 1e9,
+            "matches_device_result": max_over_ranks(0.0 if torch.equal(de_host, de_buf.cpu()) else 1.0) == 0.0}
+        del pipe_c
     e2e_launches = _lib.launch_count() - launches_e2e0
 
     log("gather")
@@ -907,11 +912,14 @@ def run_gpu_arm(args):
                     "h2d_frac_of_ceiling_with_d2h": pipe.h2d_bytes(S * 7) / (e2e_s / e2e_steps) / 1e9 / h2d_ceiling_duplex,
                     "h2d_ceiling_how": "all ranks at once: 2 x contiguous pinned cudaMemcpyAsync of the resident batch, "
                                        "max over ranks",
-                    "contiguous_upload": e2e_contig,
-                    "bound": "host-to-device copy of the live samples (PCIe Gen5 x16, ~55 GB/s per GPU in practice)",
+                    "upload_layout": "strided: live samples only" if pipe.compact else "contiguous: whole rows",
+                    "upload_probe": pipe.upload_probe,
+                    "contiguous_upload": e2e_layouts["contiguous_upload"],
+                    "strided_upload": e2e_layouts["strided_upload"],
+                    "bound": "host-to-device copy (PCIe Gen5 x16, ~55 GB/s per GPU in practice for a contiguous copy)",
                     "rank0_numa_cpus": None if numa_cpus is None else len(numa_cpus),
-                    "path": "pinned host recordings -> HostPipeline (chunked strided H2D of the live samples / fused kernel / "
-                            "D2H of DE+PSD, 3 streams) -> pinned host features"},
+                    "path": "pinned host recordings -> HostPipeline (chunked H2D in the layout its probe picked / fused kernel "
+                            "/ D2H of DE+PSD, 3 streams) -> pinned host features"},
             "gpu_launches": int(gpu_launches), "gpu_launches_e2e": int(e2e_launches),
             "roofline": roofline, "fp32_pipe": fp32_pipe, "issue_model": issue_model, "single_subject": single, "other_modes": other_modes, "next_rows": next_rows,
             "cpu_baseline": cpu,

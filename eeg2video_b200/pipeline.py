@@ -4,10 +4,12 @@ Recordings are streamed through the GPU in chunks of whole blocks: the H2D copy 
 the fused kernel on chunk i (compute stream) and the D2H copy of chunk i-1's features (second copy stream)
 overlap, so the end-to-end rate is the PCIe rate of the samples that have to cross, not the sum of the three.
 
-Only the live samples cross PCIe: a SEED-DV block is 40 concepts x (600 hint + 2000 clip) samples, so each
-channel row is uploaded with ONE strided DMA (cudaMemcpy2DAsync: 40 pieces of 8000 B out of every 10400 B) into a
-compact (blocks, channels, 40, 2000) staging tensor -- 23 % fewer bytes than the raw row -- and the kernel reads
-that layout directly (eegfe_de_psd_from_concepts).
+Only the live samples need to cross PCIe: a SEED-DV block is 40 concepts x (600 hint + 2000 clip) samples, so each
+channel row can be uploaded with ONE strided DMA (cudaMemcpy2DAsync: 40 pieces of 8000 B out of every 10400 B) into a
+compact (blocks, channels, 40, 2000) staging tensor -- 23 % fewer bytes than the raw row -- which the kernel reads
+directly (eegfe_de_psd_from_concepts).  How fast a host serves such a strided read differs from box to box (measured on
+B200 hosts of one pool: 51 GB/s on most, 29 GB/s on some, against 53-55 GB/s for a plain contiguous copy), so by
+default the pipeline times both layouts on its first chunk and keeps the faster one (compact="auto").
 """
 import torch
 
@@ -48,28 +50,66 @@ class HostPipeline:
     """Reusable staging buffers + streams for `features_from_host`.
 
     n_ch, block_len: recording geometry; chunk_blocks: blocks per in-flight chunk (two chunks are staged).
-    compact: upload only the 2000 live samples of every 2600 (needs block_len >= 104000).
+    compact: True -- upload only the 2000 live samples of every 2600 (strided DMA); False -- whole rows (contiguous DMA,
+    23 % more bytes); "auto" (default) -- time both on the first chunk of the first run() and keep the faster
+    (`self.compact` then says which, `self.upload_probe` holds the two times; decided once per device and geometry).
     """
 
-    def __init__(self, device, n_ch=62, block_len=104000, chunk_blocks=28, mode="500ms", compact=True):
+    _layout_cache = {}          # (device index, n_ch, block_len, chunk_blocks) -> (compact, probe)
+
+    def __init__(self, device, n_ch=62, block_len=104000, chunk_blocks=28, mode="500ms", compact="auto"):
         self.device = torch.device(device)
         self.mode = frontend._mode_id(mode)
         self.n_win = ops.WINDOWS_PER_CLIP[self.mode]
         self.n_ch, self.block_len, self.chunk_blocks = n_ch, block_len, chunk_blocks
-        self.compact = bool(compact)
         if block_len < CONCEPTS * CONCEPT_LEN:
             raise RuntimeError("Segment length mismatch")
+        self.upload_probe = None
+        self.compact = None if compact == "auto" else bool(compact)
         with torch.cuda.device(self.device):
-            shape = (chunk_blocks, n_ch, CONCEPTS, CLIPS_LEN) if self.compact else (chunk_blocks, n_ch, block_len)
-            self.stage = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self._cache_key = (idx, n_ch, block_len, chunk_blocks)
+            if self.compact is None and self._cache_key in HostPipeline._layout_cache:
+                self.compact, self.upload_probe = HostPipeline._layout_cache[self._cache_key]
+            # one flat buffer per stage, big enough for either layout; the layout in use is a view of it
+            per_row = block_len if self.compact in (None, False) else CONCEPTS * CLIPS_LEN
+            self._flat = [torch.empty(chunk_blocks * n_ch * per_row, dtype=torch.float32, device=self.device)
+                          for _ in range(2)]
             self.h2d = torch.cuda.Stream()
             self.d2h = torch.cuda.Stream()
             self.compute = torch.cuda.Stream()
+
+    def _stage(self, i, n_blocks, compact):
+        shape = (n_blocks, self.n_ch, CONCEPTS, CLIPS_LEN) if compact else (n_blocks, self.n_ch, self.block_len)
+        n = n_blocks * self.n_ch * (CONCEPTS * CLIPS_LEN if compact else self.block_len)
+        return self._flat[i][:n].view(shape)
+
+    def _choose_layout(self, raw_host):
+        """Time the strided and the contiguous upload of the first chunk (CUDA events on the copy stream, second of two
+        runs each) and keep the layout that takes less time."""
+        hi = min(self.chunk_blocks, raw_host.shape[0])
+        times = {}
+        with torch.cuda.stream(self.h2d):
+            for compact in (True, False):
+                self.compact = compact
+                buf = self._stage(0, hi, compact)
+                for _ in range(2):
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record(self.h2d)
+                    self._upload(buf, raw_host, 0, hi)
+                    t1.record(self.h2d)
+                    self.h2d.synchronize()
+                times[compact] = t0.elapsed_time(t1)
+        self.compact = times[True] <= times[False]
+        self.upload_probe = {"strided_live_samples_ms": times[True], "contiguous_rows_ms": times[False],
+                             "blocks": int(hi)}
+        HostPipeline._layout_cache[self._cache_key] = (self.compact, self.upload_probe)
 
     def feature_shape(self, n_blocks):
         return (n_blocks * 200, self.n_win, self.n_ch, 5)
 
     def h2d_bytes(self, n_blocks):
+        """bytes run() uploads for n_blocks blocks (after the layout has been chosen)."""
         per_row = CONCEPTS * CLIPS_LEN if self.compact else self.block_len
         return n_blocks * self.n_ch * per_row * 4
 
@@ -99,13 +139,19 @@ class HostPipeline:
             raise ValueError("raw_host must be contiguous float32 (features_from_host converts other types)")
         n_blocks = raw_host.shape[0]
         cb = self.chunk_blocks
+        if self.compact is None:
+            if n_blocks == 0:
+                self.compact = True
+            else:
+                with torch.cuda.device(self.device):
+                    self._choose_layout(raw_host)
         staged = [None, None]          # events: stage[i] free again (its kernel finished)
         with torch.cuda.device(self.device):
             with torch.cuda.stream(self.compute):      # zero-filled on the stream that ORs into it (no cross-stream race)
                 status_all = torch.zeros(1, dtype=torch.int32, device=self.device)
             for i, lo in enumerate(range(0, n_blocks, cb)):
                 hi = min(lo + cb, n_blocks)
-                buf = self.stage[i & 1][: hi - lo]
+                buf = self._stage(i & 1, hi - lo, self.compact)
                 with torch.cuda.stream(self.h2d):
                     if staged[i & 1] is not None:
                         self.h2d.wait_event(staged[i & 1])
@@ -133,7 +179,7 @@ class HostPipeline:
             return int(status_all.item())
 
 
-def features_from_host(raw_host, mode="500ms", chunk_blocks=28, device="cuda", check=True, compact=True):
+def features_from_host(raw_host, mode="500ms", chunk_blocks=28, device="cuda", check=True, compact="auto"):
     """Convenience wrapper: (.., 62, T) host tensor/array -> (de, psd) host tensors in the reference layout."""
     raw = torch.as_tensor(raw_host)
     lead = raw.shape[:-2]

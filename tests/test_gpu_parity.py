@@ -468,7 +468,7 @@ def test_from_concepts_equals_from_raw(subject):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
-@pytest.mark.parametrize("compact", (True, False))
+@pytest.mark.parametrize("compact", (True, False, "auto"))
 @pytest.mark.parametrize("block_len", (104000, 104400))
 def test_host_pipeline_matches_device_path(compact, block_len):
     from eeg2video_b200 import pipeline
@@ -477,6 +477,27 @@ def test_host_pipeline_matches_device_path(compact, block_len):
     de, psd = pipeline.features_from_host(raw.cpu(), "500ms", chunk_blocks=2, device=DEV, compact=compact)
     assert not de.is_cuda and tuple(de.shape) == (5, 40, 5, 7, 62, 5)
     assert torch.equal(de, want_de.cpu()) and torch.equal(psd, want_psd.cpu())
+
+
+def test_host_pipeline_picks_its_upload_layout_once():
+    """compact="auto": the first run() times the strided and the contiguous upload of its first chunk and keeps the
+    faster; later pipelines of the same geometry on the same device reuse the decision (no second probe)."""
+    from eeg2video_b200 import pipeline
+    pipeline.HostPipeline._layout_cache.clear()
+    raw = synth.synth_blocks(3, 32, device="cpu").pin_memory()
+    pipe = pipeline.HostPipeline(DEV, 62, 104000, chunk_blocks=2, mode="1s")
+    assert pipe.compact is None and pipe.upload_probe is None
+    de = torch.empty(pipe.feature_shape(3)).pin_memory()
+    psd = torch.empty_like(de).pin_memory()
+    assert pipe.run(raw, de, psd) == 0
+    probe = pipe.upload_probe
+    assert pipe.compact in (True, False) and probe["blocks"] == 2
+    assert pipe.compact == (probe["strided_live_samples_ms"] <= probe["contiguous_rows_ms"])
+    assert pipe.h2d_bytes(3) == 3 * 62 * (80000 if pipe.compact else 104000) * 4
+    want = frontend.de_psd_from_raw(raw.to(DEV), "1s")
+    assert torch.equal(de, want[0].cpu().reshape(de.shape)) and torch.equal(psd, want[1].cpu().reshape(psd.shape))
+    again = pipeline.HostPipeline(DEV, 62, 104000, chunk_blocks=2, mode="2s")
+    assert again.compact == pipe.compact and again.upload_probe is probe
 
 
 def test_host_pipeline_zero_power_flag():
