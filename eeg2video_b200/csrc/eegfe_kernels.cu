@@ -390,13 +390,15 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
     // bits 0..13: window offset in the slot (floats), 14..24: staging index, 25..30: row in tile
     thread_meta[tid] = (row * C::kRowStride + w * C::kHop) | (((w * C::kRows + row) * 5) << 14) | (row << 25);
   }
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < C::kSlots; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], C::kGroupWarps);
-      armed[s] = 0;
-    }
+  // per-slot state, set up by ALL of warp 0 (lane l: slot l % kSlots; four lanes write the same values): no warp may
+  // diverge in front of the block barrier -- ptxas does not always reconverge it there and BAR.SYNC does not either
+  // (eegfe_stream.cuh).  `tid < kWorkers` above is warp-uniform (kWorkers is a multiple of 32).
+  static_assert(C::kWorkers % 32 == 0 && (C::kSlots & (C::kSlots - 1)) == 0 && C::kSlots <= 32, "set-up by whole warps");
+  if (tid < 32) {
+    const int sl = tid % C::kSlots;
+    mbar_init(&full_bar[sl], 1);
+    mbar_init(&empty_bar[sl], C::kGroupWarps);
+    armed[sl] = 0;
     mbar_fence_init();
   }
   __syncthreads();
@@ -825,15 +827,20 @@ static int launch_stream(const Job& job, cudaStream_t stream)
     }
   } else if (job.row_align < 16) {
     // rows TMA cannot start a copy at -- kernels of their own, the default kernel carries none of their code.
-    // Sliding 500 ms windows whose rows are 8-byte aligned (and padded in shared memory): TMA copies of the aligned
-    // span around each row, read shifted by 0 or 2 floats (still LDS.64).  Everything else -- 4-byte rows, pre-cut
-    // windows (dense rows, nothing to shift into) -- cp.async.
-    if (kCanNorm && job.row_align == 8) {
-      if constexpr (kCanNorm) {
+    // Sliding 500 ms windows (rows padded in shared memory): TMA copies of the aligned span around each row, read
+    // shifted (LDS.64 when every row is 8-byte aligned, else LDS.32); pre-cut windows (dense rows, nothing to shift
+    // into): cp.async.
+    if constexpr (kCanNorm) {
+      if (job.row_align == 8) {
         static std::atomic<unsigned long long> configured_shift2{0};
         const int rc = configure_smem(configured_shift2, de_psd_stream_kernel<SC, false, false, 2>, SC::kSmemBytes);
         if (rc != 0) return rc;
         de_psd_stream_kernel<SC, false, false, 2><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
+      } else {
+        static std::atomic<unsigned long long> configured_shift1{0};
+        const int rc = configure_smem(configured_shift1, de_psd_stream_kernel<SC, false, false, 1>, SC::kSmemBytes);
+        if (rc != 0) return rc;
+        de_psd_stream_kernel<SC, false, false, 1><<<grid, SC::kThreads, SC::kSmemBytes, stream>>>(job);
       }
     } else {
       static std::atomic<unsigned long long> configured_small{0};

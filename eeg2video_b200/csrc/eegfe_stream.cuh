@@ -245,9 +245,7 @@ __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const flo
 // SMALL: rows fetched with cp.async (rows that are only 4-byte aligned; pre-cut windows that are not 16-byte aligned:
 //        their rows have no padding to shift into).
 // SHIFT: rows fetched as the aligned span around them and read k floats in -- 2: every k is 0 or 2 (8-byte aligned
-//        rows), windows still read with LDS.64.  (1: any k, scalar LDS.32 -- compiles, and HANGS on B200 on every
-//        input, k = 0 included, while the same loader with LDS.64 reads and the same scalar reads in the ring kernel
-//        work; control flow of the two SASS listings is identical.  Not instantiated; cause not found.  DESIGN.md 4.1.)
+//        rows), windows still read with LDS.64; 1: any k, scalar LDS.32.
 template <class SC, bool NORM, bool SMALL = false, int SHIFT = 0>
 __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __grid_constant__ Job job)
 {
@@ -271,8 +269,11 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
   __shared__ unsigned next_pass;
   __shared__ float norm_tab[NORM ? 2 * kNormTableChannels : 2];
   if constexpr (NORM) {
+    // every thread runs the same number of steps (surplus threads repeat the last channel): no warp diverges in front of
+    // the block barrier below -- see the set-up comment
     if (job.n_ch <= kNormTableChannels)
-      for (unsigned i = threadIdx.x; i < job.n_ch; i += blockDim.x) {
+      for (unsigned i0 = 0; i0 < job.n_ch; i0 += blockDim.x) {
+        const unsigned i = i0 + threadIdx.x < job.n_ch ? i0 + threadIdx.x : job.n_ch - 1;
         norm_tab[i] = job.norm_scale[i];
         norm_tab[kNormTableChannels + i] = job.norm_mean[i];
       }
@@ -289,26 +290,37 @@ __global__ void __launch_bounds__(SC::kThreads, 1) de_psd_stream_kernel(const __
     return static_cast<int>(left < C::kRows ? left : C::kRows);
   };
 
-  if (tid < C::kUnits) {
-    int row = tid, w = 0;
+  // ---- set-up, written so that NO warp diverges before the block barrier.
+  // Seen twice on B200 with this kernel (an out-of-line loader call; scalar shared-memory reads): for `if (tid < 112)` /
+  // `if (tid == 0)` blocks ptxas emits, in some instantiations, no BSSY / BSYNC pair around the branch -- the lane groups
+  // of warp 3 / warp 0 then reach BAR.SYNC separately, are NOT reconverged by it, and run the code behind it (which
+  // keeps per-warp state in uniform registers) as independent groups: the kernel hangs on every input.  A
+  // `__syncwarp()` in front of the barrier does not help (ptxas drops it as redundant).  All eight SASS listings that
+  // hung lack exactly that BSYNC, all that worked have it (tests/test_abi.py keeps watch).  So: whole
+  // warps only -- the unit table is filled by four full warps (the surplus lanes repeat its last entry) and the
+  // per-slot state by all of warp 0 (four lanes write the same values to each slot).
+  constexpr int kMetaThreads = (C::kUnits + 31) / 32 * 32;
+  static_assert(kMetaThreads <= C::kThreads && C::kSlots <= 32, "set-up by whole warps");
+  if (tid < kMetaThreads) {                                    // warp-uniform
+    const int u = tid < C::kUnits ? tid : C::kUnits - 1;
+    int row = u, w = 0;
     if constexpr (C::kLaneMap) {
       static_assert(!C::kLaneMap || C::kUnits == 112, "lane map of 16-row x 7-window tiles");
-      const int code = c_lane_map_500_r16[tid];
+      const int code = c_lane_map_500_r16[u];
       row = code >> 3;
       w = code & 7;
     }
     // bits 0..13: window offset in the slot (floats), 14..24: staging index, 25..30: row in tile
-    unit_meta[tid] = (row * C::kRowStride + w * C::kHop) | (((w * C::kRows + row) * 5) << 14) | (row << 25);
+    unit_meta[u] = (row * C::kRowStride + w * C::kHop) | (((w * C::kRows + row) * 5) << 14) | (row << 25);
   }
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < C::kSlots; ++s) {
-      mbar_init(&full_bar[s], SMALL ? 32 : 1);
-      consumed[s] = 0;
-      staged[s] = 0;
-      drained[s] = 0;
-      armed[s] = 0;
-    }
+  if (tid < 32) {                                              // warp-uniform; lane l sets up slot l % kSlots
+    static_assert((C::kSlots & (C::kSlots - 1)) == 0, "every lane of warp 0 repeats the set-up of one slot");
+    const int sl = tid % C::kSlots;                            // (the same values from four lanes: no lane is idle)
+    mbar_init(&full_bar[sl], SMALL ? 32 : 1);
+    consumed[sl] = 0;
+    staged[sl] = 0;
+    drained[sl] = 0;
+    armed[sl] = 0;
     next_pass = 0;
     mbar_fence_init();
   }

@@ -50,27 +50,12 @@ def de_psd_from_raw(raw: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.T
         de = torch.empty((n_blocks * 200, n_win, n_ch, 5), dtype=torch.float32, device=raw.device)
         psd = torch.empty_like(de)
         status = torch.zeros(1, dtype=torch.int32, device=raw.device)
-        # Rows that are not 16-byte aligned (an odd block length or stride) cannot be the source of a TMA bulk copy.
-        # libeegfe then copies the 16-byte aligned span around each row and reads it shifted (1 s / 2 s modes; 500 ms
-        # mode when the rows are 8-byte aligned) -- one launch, no extra pass.  500 ms mode with 4-byte rows: the library's
-        # cp.async loader manages 4.9 G channel-windows/s (measured, 24 subjects) against 5.8 G for re-aligning the clips
-        # first (one extra HBM pass through a bounded scratch buffer) and running the TMA kernel, so that is done here.
-        even = raw.data_ptr() % 8 == 0 and raw.stride(0) % 2 == 0 and raw.stride(1) % 2 == 0
-        if mode != _lib.MODE_500MS or even or n_blocks == 0 or t_len < 40 * 2600:
-            _lib.check(lib.eegfe_de_psd_from_raw(
-                raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), mode,
-                de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
-        else:
-            chunk = max(1, min(n_blocks, 28))
-            scratch = torch.empty((chunk * 200, n_ch, 400), dtype=torch.float32, device=raw.device)
-            for lo in range(0, n_blocks, chunk):
-                nb = min(chunk, n_blocks - lo)
-                part = raw[lo:lo + nb]
-                _lib.check(lib.eegfe_segment_clips(part.data_ptr(), _lib.DTYPE_F32, nb, n_ch, t_len, raw.stride(0),
-                                                   raw.stride(1), 200, scratch.data_ptr(), _stream(raw)))
-                _lib.check(lib.eegfe_de_psd_from_clips(scratch.data_ptr(), nb * 200, n_ch, mode,
-                                                       de[lo * 200:].data_ptr(), psd[lo * 200:].data_ptr(),
-                                                       status.data_ptr(), _stream(raw)))
+        # Rows that are not 16-byte aligned (an odd block length or stride) cannot be the source of a TMA bulk copy:
+        # libeegfe then copies the 16-byte aligned span around each row and reads it shifted (separate instantiations of
+        # the kernels) -- one launch, no extra pass, no workspace.
+        _lib.check(lib.eegfe_de_psd_from_raw(
+            raw.data_ptr(), n_blocks, n_ch, t_len, raw.stride(0), raw.stride(1), mode,
+            de.data_ptr(), psd.data_ptr(), status.data_ptr(), _stream(raw)))
     return de, psd, status
 
 

@@ -113,3 +113,45 @@ def test_hot_kernels_stay_near_the_instruction_cache_size():
     too_big = {k: v for k, v in hot.items() if v > 36 * 1024 and not shifted.search(k)}
     assert all(v <= 40 * 1024 for v in hot.values()), hot
     assert not too_big, too_big
+
+
+def test_no_warp_diverges_in_front_of_the_block_barrier():
+    """Seen twice on B200: an instantiation of the streaming kernel in which ptxas emitted no BSSY / BSYNC pair around the
+    set-up `if (tid == 0)` / `if (tid < 112)` hung on every input -- the lane groups of the split warps are not
+    reconverged by BAR.SYNC and then run code that keeps per-warp state in uniform registers as independent groups
+    (DESIGN.md 4.1).  The set-up is now written with whole-warp conditions only.  Tripwire on the SASS: in front of the
+    first BAR.SYNC of every feature kernel, predicated branches outside a BSSY region are at most the known whole-warp
+    ones (tile guard, `tid < kMetaThreads` / `tid < kWorkers`, `tid < 32`, the GLMNet table guard)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    listing = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    kernels, name = {}, None
+    for line in listing.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            kernels[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,5}\*/", line):
+            kernels[name].append(line)
+    checked = 0
+    for k, body in kernels.items():
+        if "de_psd_kernel" not in k and "de_psd_stream_kernel" not in k:
+            continue
+        depth, bare = 0, 0
+        for line in body:
+            if "BAR.SYNC" in line:
+                break
+            if "BSSY" in line:
+                depth += 1
+            elif "BSYNC" in line:
+                depth -= 1
+            elif re.search(r"@!?P\d\s+BRA\b", line) and depth == 0:
+                bare += 1
+        else:
+            pytest.fail(f"{k}: no block barrier found")
+        assert bare <= 4, (k, bare)
+        checked += 1
+    assert checked >= 10

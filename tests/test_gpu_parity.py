@@ -423,10 +423,8 @@ def test_unaligned_block_length_uses_fallback_loader():
 def test_rows_of_every_alignment(mode, t_len, offset):
     """Rows that start 4, 8 or 12 bytes off a 16-byte boundary -- an odd block length (the offset then changes from
     row to row) or a view that starts inside a buffer of pitch 104004 (the same offset for every row).  TMA cannot start a copy there:
-    the kernels copy the aligned span around each row and read it shifted (1 s / 2 s: any offset; 500 ms: 8-byte
-    offsets), the streaming kernel (500 ms) falls back to cp.async for 4-byte offsets.  Called through the C ABI
-    directly and through the op (which re-aligns 4-byte rows in 500 ms mode); all must equal the result on an aligned
-    copy, bit for bit.  37 channels: ragged tiles."""
+    the kernels copy the 16-byte aligned span around each row and read it shifted.  Called through the C ABI directly
+    and through the op; both must equal the result on an aligned copy, bit for bit.  37 channels: ragged tiles."""
     base = synth.synth_blocks(1, 9, device=DEV, channels=37, block_len=t_len + offset)
     raw = base[..., offset:]
     assert raw.data_ptr() % 16 == 4 * offset

@@ -78,9 +78,8 @@ def main():
     bad += run_case("glmnet inputs", max(10, args.launches // 3),
                     lambda i: (ops.glmnet_inputs_from_raw(raw[:14 - (i % 3)], scale, center)[:3], 14 - (i % 3)),
                     lambda n: n * 200)
-    # rows TMA cannot start at (8-byte rows: T = 104002, 4-byte rows: T = 104001): the streaming kernel's cp.async
-    # instantiation and the ring kernel's shifted-span instantiation, through the C ABI directly
-    # (ops.de_psd_from_raw re-aligns 4-byte rows in 500 ms mode instead)
+    # rows TMA cannot start at (8-byte rows: T = 104002, 4-byte rows: T = 104001): the shifted-span instantiations
+    # of both kernels, through the C ABI directly
     from eeg2video_b200 import _lib
     lib = _lib.load()
     for t_len in (104002, 104001):
