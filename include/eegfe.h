@@ -71,6 +71,11 @@ int eegfe_windows_per_clip(int mode);
  * de, psd      float32 [n_blocks * 200][n_windows][n_ch][5]; clip index = (block * 40 + concept) * 5 + repetition.
  * No clip tensor is materialised: windows are cut by index arithmetic, clip (c, r) starting at sample
  * c * 2600 + 600 + r * 400.
+ * Alignment: any (rows need only be float-aligned).  Rows that start on 16-byte boundaries are fetched by TMA bulk
+ * copies; for other rows (block_len or a stride not a multiple of 4, a base pointer inside a buffer) the 16-byte
+ * aligned span AROUND each row is fetched instead -- up to 12 bytes before its first and after its last sample -- and
+ * read shifted.  Those bytes must be readable: true whenever the buffer is (part of) an allocation that starts and
+ * ends on 16-byte boundaries (cudaMalloc, every framework allocator).
  */
 int eegfe_de_psd_from_raw(const float* raw, int64_t n_blocks, int n_ch, int64_t block_len,
                           int64_t block_stride, int64_t ch_stride, int mode,
