@@ -51,7 +51,7 @@ struct Job {
   unsigned d1_magic, d2_magic;   // the same for d1 and d2 (set by launch<>; used by the streaming kernel's hot paths)
   long long t_extent;     // valid elements of a channel row (tensor-map bound of the time axis); 0 = unknown
   int row_align;            // bytes every row start is a multiple of: 16 (TMA bulk copies of the rows themselves), else 8
-                            // or 4 (streaming kernel: cp.async loader; ring kernel: TMA copies of the aligned span, SHIFT)
+                            // or 4 (TMA copies of the aligned span around each row, read shifted: SHIFT instantiations)
   unsigned tiles_per_clip;  // > 0: tiles never straddle clips (tile = kRows channels of one clip), fetched as tensor boxes
   int rows_tma;             // pre-cut windows in a dense / uniformly strided 2-D array: tile = tensor box of kRows rows
   // optional second product of the 500 ms kernel (GLMNet raw branch): clips_norm[row][400] = (x - mean[ch]) * scale[ch]
@@ -336,10 +336,11 @@ namespace eegfe {
 // it can fetch the 16-byte aligned span AROUND the row -- from the row start rounded down to the row end rounded up,
 // at most 16 bytes more, which is exactly the slot's row padding -- so the row lands k = 0..3 floats into its
 // shared-memory row.  The producer notes k per row, the worker adds it to its window pointer and reads scalar
-// (LDS.32) instead of LDS.128.  Same HBM traffic and copy count as the aligned kernel, no second pass.  The span stays
+// (LDS.32; SHIFT = 2, every row 8-byte aligned: LDS.64) instead of LDS.128.  Same HBM traffic and copy count as the
+// aligned kernel, no second pass.  The span stays
 // inside the caller's allocation as long as that starts and ends on 16-byte boundaries (cudaMalloc, torch: always).
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, bool SHIFT = false, bool TENSOR = false>
+template <class C, int SHIFT = 0, bool TENSOR = false>
 __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(const __grid_constant__ Job job)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm) de_psd_kernel(cons
   __shared__ unsigned armed[C::kSlots];
   __shared__ unsigned char row_shift[SHIFT ? C::kSlots : 1][SHIFT ? C::kRows : 1];   // k of every row in flight
   static_assert(!SHIFT || (C::kRowStride >= C::kLoad + 4 && C::kRows <= 32), "a shifted row needs 16 bytes of padding");
-  constexpr int kVec = SHIFT ? 1 : C::kVec;
+  constexpr int kVec = SHIFT == 1 ? 1 : (SHIFT == 2 ? 2 : C::kVec);     // SHIFT 2: every k is 0 or 2 -> LDS.64
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -954,8 +955,8 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
   }
   unsigned n_tiles = (job.total_rows + C::kRows - 1) / C::kRows;
   if (!aligned16 && job.norm_out == nullptr) {
-    // rows that are only 8- / 4-byte aligned: the streaming kernel with its cp.async loader, the ring kernel with TMA
-    // copies of the 16-byte aligned span around each row (SHIFT instantiation)
+    // rows that are only 8- / 4-byte aligned: TMA copies of the 16-byte aligned span around each row, read shifted
+    // (SHIFT instantiations of both kernels)
     const bool even = reinterpret_cast<uintptr_t>(job.in) % 8 == 0 && job.base % 2 == 0 && job.s0 % 2 == 0 &&
                       job.s1 % 2 == 0 && job.s2 % 2 == 0 && job.ch_stride % 2 == 0;
     job.row_align = even ? 8 : 4;
@@ -981,15 +982,20 @@ static int launch(const Job& job_in, bool aligned16, cudaStream_t stream)
       if (job.tiles_per_clip != 0 || job.rows_tma != 0) {
         if constexpr (C::kLoad == 200 && C::kHann == kHannTwoSec) {
           static std::atomic<unsigned long long> configured_tensor{0};
-          const int rc = configure_smem(configured_tensor, de_psd_kernel<C, false, true>, C::kSmemBytes);
+          const int rc = configure_smem(configured_tensor, de_psd_kernel<C, 0, true>, C::kSmemBytes);
           if (rc != 0) return rc;
-          de_psd_kernel<C, false, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+          de_psd_kernel<C, 0, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
         }
-      } else if (job.row_align < 16) {
-        static std::atomic<unsigned long long> configured_shift{0};
-        const int rc = configure_smem(configured_shift, de_psd_kernel<C, true>, C::kSmemBytes);
+      } else if (job.row_align == 8) {
+        static std::atomic<unsigned long long> configured_shift2{0};
+        const int rc = configure_smem(configured_shift2, de_psd_kernel<C, 2>, C::kSmemBytes);
         if (rc != 0) return rc;
-        de_psd_kernel<C, true><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+        de_psd_kernel<C, 2><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
+      } else if (job.row_align < 16) {
+        static std::atomic<unsigned long long> configured_shift1{0};
+        const int rc = configure_smem(configured_shift1, de_psd_kernel<C, 1>, C::kSmemBytes);
+        if (rc != 0) return rc;
+        de_psd_kernel<C, 1><<<grid, C::kThreads, C::kSmemBytes, stream>>>(job);
       } else {
         const int rc = configure_smem(configured, de_psd_kernel<C>, C::kSmemBytes);
         if (rc != 0) return rc;
