@@ -13,7 +13,8 @@
 //                                             16 identical warps draw passes from a counter, tile duties fall to the
 //                                             last finisher
 //   this file          de_psd_kernel          1 s / 2 s windows: HBM-bound; producer warps + worker groups on a ring
-//                      (both)                 rows that are only 8- / 4-byte aligned: cp.async loader instead of TMA
+//                      (both)                 rows that are only 8- / 4-byte aligned: TMA copies of the 16-byte aligned
+//                                             span around each row, read shifted (SHIFT instantiations)
 //                      gather / sliding-window / statistics kernels for the materialising and "next row" entry points
 //
 // C ABI: include/eegfe.h.  Reference semantics: see the citations in that header and in bandpower.cuh.

@@ -103,7 +103,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // constants cannot stay live across a call and are re-materialised every pass); -DEEGFE_STREAM_DUTY=__noinline__
 // builds the out-of-line form for comparison.
 
-// cp.async of BYTES (4 or 8) per lane: rows that are not 16-byte aligned cannot ride on TMA bulk copies
+// cp.async of BYTES (4 or 8) per lane (pre-cut windows whose rows are not 16-byte aligned; everything else that is
+// misaligned arrives as a TMA copy of the aligned span around it, see stream_load_tile)
 template <int BYTES>
 __device__ __forceinline__ void cp_async_small(void* dst_smem, const void* src_gmem)
 {
@@ -118,8 +119,8 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
 {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Rows that are only 8- or 4-byte aligned (job.row_align; an odd block length or stride) cannot ride on TMA bulk copies:
-// the SMALL instantiation of the kernel fetches them with 8- / 4-byte cp.async (LDGSTS), one row per step, lanes side
+// Dense rows (pre-cut windows) that are only 8- or 4-byte aligned (job.row_align) cannot ride on TMA bulk copies and
+// have no row padding to shift into: the SMALL instantiation of the kernel fetches them with 8- / 4-byte cp.async (LDGSTS), one row per step, lanes side
 // by side; every lane's arrival on the slot's barrier (32 per phase in this instantiation) fires when its copies have
 // landed.  It is a separate kernel so that the TMA kernel's hot loop carries none of this code.
 template <class SC>
@@ -242,8 +243,8 @@ __device__ __forceinline__ void stream_store_norm_rows(const Job& job, const flo
   }
 }
 
-// SMALL: rows fetched with cp.async (rows that are only 4-byte aligned; pre-cut windows that are not 16-byte aligned:
-//        their rows have no padding to shift into).
+// SMALL: rows fetched with cp.async (pre-cut windows that are not 16-byte aligned: their rows have no padding to
+//        shift into).
 // SHIFT: rows fetched as the aligned span around them and read k floats in -- 2: every k is 0 or 2 (8-byte aligned
 //        rows), windows still read with LDS.64; 1: any k, scalar LDS.32.
 template <class SC, bool NORM, bool SMALL = false, int SHIFT = 0>

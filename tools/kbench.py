@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--launches", type=int, default=20)
     ap.add_argument("--peak", type=float, default=6541.8)
     ap.add_argument("--block-len", type=int, default=104000,
-                    help="samples per channel row; 104001 / 104002 make the rows 4- / 8-byte aligned only (shifted TMA spans / cp.async loader)")
+                    help="samples per channel row; 104001 / 104002 make the rows 4- / 8-byte aligned only (TMA copies of the aligned span, read shifted)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128), 0 = leave")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
