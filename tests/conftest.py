@@ -89,6 +89,21 @@ def hostemu():
         with np.errstate(divide="ignore"):
             de = np.log2(np.float32(100.0) * psd.astype(np.float32)).astype(np.float64)
         return de, psd.astype(np.float64)
+
+    def band_energy(x, shift=None, vec=None):
+        """raw float32 band energies (n, 5); with shift / vec: the shifted-span read path of the kernels."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        e = np.zeros((x.shape[0], 5), dtype=np.float32)
+        if shift is None:
+            rc = dll.hostemu_band_energy(x.ctypes.data, x.shape[0], x.shape[1], e.ctypes.data)
+        else:
+            rc = dll.hostemu_band_energy_shifted(x.ctypes.data, x.shape[0], x.shape[1], shift, vec, e.ctypes.data)
+        assert rc == 0
+        return e
+    dll.hostemu_band_energy_shifted.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_void_p]
+    dll.hostemu_band_energy_shifted.restype = ctypes.c_int
+    band_features.band_energy = band_energy
     return band_features
 
 

@@ -36,4 +36,34 @@ int hostemu_band_energy(const float* x, int64_t n_windows, int len, float* energ
   return 0;
 }
 
+// The shifted-span form of the kernels (rows that are not 16-byte aligned): the window starts `shift` floats (0..3) into
+// a 16-byte aligned row and is read with scalar loads (vec = 1) or, for even shifts, 64-bit loads (vec = 2).
+int hostemu_band_energy_shifted(const float* x, int64_t n_windows, int len, int shift, int vec, float* energy)
+{
+  if (shift < 0 || shift > 3 || (vec != 1 && vec != 2) || (vec == 2 && (shift & 1))) return 1;
+  alignas(16) float buf[208];
+  for (int64_t w = 0; w < n_windows; ++w) {
+    const float* row = x + w * len;
+    float e[5];
+    for (int i = 0; i < 208; ++i) buf[i] = -12345.0f;                 // anything outside the window must not matter
+    const int live = len == 100 ? 100 : 200;
+    for (int i = 0; i < live; ++i) buf[shift + i] = row[i];
+    const float* win = buf + shift;
+    if (len == 100) {
+      if (vec == 1) eegfe::window_band_energy<4, eegfe::kHannHalfSec, 1>(win, e);
+      else eegfe::window_band_energy<4, eegfe::kHannHalfSec, 2>(win, e);
+    } else if (len == 200) {
+      if (vec == 1) eegfe::window_band_energy<8, eegfe::kHannOneSec, 1>(win, e);
+      else eegfe::window_band_energy<8, eegfe::kHannOneSec, 2>(win, e);
+    } else if (len == 400) {
+      if (vec == 1) eegfe::window_band_energy<8, eegfe::kHannTwoSec, 1>(win, e);
+      else eegfe::window_band_energy<8, eegfe::kHannTwoSec, 2>(win, e);
+    } else {
+      return 1;
+    }
+    for (int b = 0; b < 5; ++b) energy[w * 5 + b] = e[b];
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -87,3 +87,18 @@ def test_core_power_of_two_scaling_is_exact(hostemu):
     _, p1 = hostemu(x)
     _, p2 = hostemu(2 * x)
     assert np.array_equal(4 * p1, p2)
+
+
+@pytest.mark.parametrize("length", (100, 200, 400))
+def test_shifted_reads_feed_identical_arithmetic(hostemu, length):
+    """The kernels' shifted-span form (rows that are not 16-byte aligned) reads the window 0..3 floats into its
+    shared-memory row with scalar loads, or with 64-bit loads when the offset is even: same samples, same operations,
+    hence the same bits as the aligned 64- / 128-bit read path -- and nothing outside the window is touched (the
+    emulation poisons it)."""
+    rng = np.random.default_rng(length)
+    x = (30 * rng.standard_normal((64, length))).astype(np.float32)
+    want = hostemu.band_energy(x)
+    for shift in range(4):
+        assert np.array_equal(hostemu.band_energy(x, shift, 1), want), (shift, 1)
+        if shift % 2 == 0:
+            assert np.array_equal(hostemu.band_energy(x, shift, 2), want), (shift, 2)
